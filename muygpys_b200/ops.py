@@ -1,0 +1,391 @@
+"""Thin torch-tensor wrappers over the C ABI: device memory and streams only.
+
+Every function takes/returns CUDA float64 / int64 tensors, launches on torch's
+current stream and never synchronises.  There is no CPU path: tensors that are
+not on a CUDA device raise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import torch
+
+from . import _lib as L
+
+f64 = torch.float64
+i64 = torch.int64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise L.MgpError(
+            f"{name} lives on {t.device}: muygpys_b200 kernels only run on CUDA tensors "
+            "(no CPU fallback)"
+        )
+
+
+def fdev(t, name="tensor") -> torch.Tensor:
+    """float64, contiguous, CUDA."""
+    _need_cuda(t, name)
+    if t.dtype != f64:
+        t = t.to(f64)
+    return t.contiguous()
+
+
+def idev(t, name="indices") -> torch.Tensor:
+    """int64, contiguous, CUDA."""
+    _need_cuda(t, name)
+    if t.dtype != i64:
+        t = t.to(i64)
+    return t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _host_doubles(vals: Sequence[float]):
+    arr = (C.c_double * len(vals))(*[float(v) for v in vals])
+    return arr
+
+
+def _ls_list(length_scale) -> list:
+    if isinstance(length_scale, torch.Tensor):
+        length_scale = length_scale.detach().cpu().reshape(-1).tolist()
+    try:
+        return [float(v) for v in length_scale]
+    except TypeError:
+        return [float(length_scale)]
+
+
+def as_2d(x: torch.Tensor) -> torch.Tensor:
+    """The reference treats 1-D feature arrays as (n,1) (S/neighbors.py:84-85)."""
+    return x[:, None] if x.dim() == 1 else x
+
+
+# --------------------------------------------------------------------------
+# fused path
+# --------------------------------------------------------------------------
+def fused_posterior(
+    train_x: torch.Tensor,
+    query_x: torch.Tensor,
+    query_idx: Optional[torch.Tensor],
+    nn_idx: torch.Tensor,
+    train_y: Optional[torch.Tensor],
+    *,
+    kernel_id: int,
+    metric_id: int,
+    length_scale,
+    noise: Union[float, torch.Tensor] = 0.0,
+    scale: float = 1.0,
+    want_mean: bool = True,
+    want_var: bool = True,
+    want_yky: bool = False,
+    want_coeffs: bool = False,
+    want_status: bool = False,
+):
+    """One launch of K1 over a batch of neighbourhoods.  Returns a dict of tensors.
+
+    `noise` is a python float (homoscedastic) or a (b,k) tensor (heteroscedastic).
+    mean is (b,r), var (b,), yky (b,), coeffs (b,k,r), status (b,) int32.
+    """
+    lib = L.lib()
+    train_x = as_2d(fdev(train_x, "train_features"))
+    query_x = as_2d(fdev(query_x, "test_features"))
+    nn_idx = idev(nn_idx, "nn_indices")
+    if nn_idx.dim() != 2:
+        raise ValueError(f"nn_indices must be (batch_count, nn_count), not {tuple(nn_idx.shape)}")
+    b, k = nn_idx.shape
+    n, d = train_x.shape
+    t = query_x.shape[0]
+    if query_x.shape[1] != d:
+        raise ValueError(f"feature counts differ: {query_x.shape[1]} vs {d}")
+    if query_idx is not None:
+        query_idx = idev(query_idx, "indices")
+        if query_idx.shape[0] != b:
+            raise ValueError("indices and nn_indices disagree on batch_count")
+    elif b > t:
+        raise ValueError("more neighbourhood rows than query points")
+    r = 1
+    y2 = None
+    if train_y is not None:
+        y2 = fdev(train_y, "train_targets")
+        y2 = y2[:, None] if y2.dim() == 1 else y2
+        if y2.shape[0] != n:
+            raise ValueError("train_targets and train_features disagree on train_count")
+        y2 = y2.contiguous()
+        r = y2.shape[1]
+    dev = train_x.device
+    ls = _ls_list(length_scale)
+    ls_host = _host_doubles(ls)
+    noise_bk = None
+    noise_val = 0.0
+    if isinstance(noise, torch.Tensor) and noise.dim() > 0:
+        noise_bk = fdev(noise, "noise")
+        if tuple(noise_bk.shape) != (b, k):
+            raise ValueError(f"heteroscedastic noise must be (batch_count, nn_count)={b, k}")
+    else:
+        noise_val = float(noise)
+    out = {}
+    if want_mean:
+        out["mean"] = torch.empty((b, r), dtype=f64, device=dev)
+    if want_var:
+        out["var"] = torch.empty((b,), dtype=f64, device=dev)
+    if want_yky:
+        out["yky"] = torch.empty((b,), dtype=f64, device=dev)
+    if want_coeffs:
+        out["coeffs"] = torch.empty((b, k, r), dtype=f64, device=dev)
+    if want_status:
+        out["status"] = torch.empty((b,), dtype=torch.int32, device=dev)
+    p = L.MgpProblem(
+        train_x=_p(train_x), query_x=_p(query_x), query_idx=_p(query_idx), nn_idx=_p(nn_idx),
+        train_y=_p(y2), n=n, t=t, b=b, k=k, d=d, r=r, kernel_id=int(kernel_id),
+        metric_id=int(metric_id), length_scale_count=len(ls),
+        length_scale=C.cast(ls_host, C.POINTER(C.c_double)), noise=noise_val,
+        noise_bk=_p(noise_bk), scale=float(scale), mean=_p(out.get("mean")),
+        var=_p(out.get("var")), yky=_p(out.get("yky")), coeffs=_p(out.get("coeffs")),
+        status=_p(out.get("status")),
+    )
+    ws = None
+    ws_bytes = lib.mgp_fused_workspace_bytes(C.byref(p))
+    if ws_bytes:
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    L.check(lib.mgp_fused_posterior(C.byref(p), _p(ws), ws_bytes, _stream()))
+    return out
+
+
+def fast_mean(train_x, query_x, query_idx, nn_idx, coeff_row, coeffs, *, kernel_id, metric_id,
+              length_scale) -> torch.Tensor:
+    """K4: mean (b,r) = sum_j kernel(|q - x_nn_j|) * coeffs[coeff_row, j, :]."""
+    lib = L.lib()
+    train_x = as_2d(fdev(train_x))
+    query_x = as_2d(fdev(query_x))
+    nn_idx = idev(nn_idx)
+    b, k = nn_idx.shape
+    n, d = train_x.shape
+    coeffs = fdev(coeffs, "coeffs_tensor")
+    if coeffs.dim() == 2:
+        coeffs = coeffs[:, :, None].contiguous()
+    if coeffs.shape[1] != k:
+        raise ValueError("coeffs_tensor and nn_indices disagree on nn_count")
+    r = coeffs.shape[2]
+    query_idx = None if query_idx is None else idev(query_idx)
+    coeff_row = None if coeff_row is None else idev(coeff_row)
+    ls = _ls_list(length_scale)
+    ls_host = _host_doubles(ls)
+    mean = torch.empty((b, r), dtype=f64, device=train_x.device)
+    p = L.MgpProblem(
+        train_x=_p(train_x), query_x=_p(query_x), query_idx=_p(query_idx), nn_idx=_p(nn_idx),
+        train_y=None, n=n, t=query_x.shape[0], b=b, k=k, d=d, r=r, kernel_id=int(kernel_id),
+        metric_id=int(metric_id), length_scale_count=len(ls),
+        length_scale=C.cast(ls_host, C.POINTER(C.c_double)), noise=0.0, noise_bk=None, scale=1.0,
+        mean=_p(mean), var=None, yky=None, coeffs=None, status=None,
+    )
+    L.check(lib.mgp_fast_mean(C.byref(p), _p(coeff_row), _p(coeffs), _stream()))
+    return mean
+
+
+# --------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------
+def loss_partials(loss_id, pred, targets, var=None, yky=None, scale_dev=None,
+                  boundary_scale=1.0, partials=None) -> torch.Tensor:
+    """Accumulate an MGP_PARTIALS record (device tensor of 8 doubles)."""
+    lib = L.lib()
+    pred = fdev(pred, "predictions")
+    b = pred.shape[0]
+    r = 1 if pred.dim() == 1 else pred.shape[1]
+    dev = pred.device
+    if targets is not None:
+        targets = fdev(targets, "targets")
+        if targets.numel() != pred.numel():
+            raise ValueError("predictions and targets differ in size")
+    var = None if var is None else fdev(var, "variances")
+    yky = None if yky is None else fdev(yky)
+    scale_dev = None if scale_dev is None else fdev(scale_dev)
+    if partials is None:
+        partials = torch.zeros((L.MGP_PARTIALS,), dtype=f64, device=dev)
+    ws_bytes = lib.mgp_loss_workspace_bytes(b, r)
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
+    L.check(lib.mgp_loss_partials(int(loss_id), _p(pred), _p(targets), _p(var), _p(yky),
+                                  _p(scale_dev), float(boundary_scale), b, r, _p(partials),
+                                  _p(ws), ws_bytes, _stream()))
+    return partials
+
+
+# --------------------------------------------------------------------------
+# KNN
+# --------------------------------------------------------------------------
+def knn(train, queries, k, self_idx=None):
+    lib = L.lib()
+    train = as_2d(fdev(train, "train"))
+    queries = as_2d(fdev(queries, "queries"))
+    n, d = train.shape
+    q = queries.shape[0]
+    if queries.shape[1] != d:
+        raise ValueError(f"query feature count {queries.shape[1]} != train feature count {d}")
+    self_idx = None if self_idx is None else idev(self_idx)
+    out_idx = torch.empty((q, k), dtype=i64, device=train.device)
+    out_d2 = torch.empty((q, k), dtype=f64, device=train.device)
+    ws_bytes = lib.mgp_knn_workspace_bytes(n, q, d, k)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=train.device) if ws_bytes else None
+    L.check(lib.mgp_knn(_p(train), n, _p(queries), q, d, int(k), 0 if self_idx is None else 1,
+                        _p(self_idx), _p(out_idx), _p(out_d2), _p(ws), ws_bytes, _stream()))
+    return out_idx, out_d2
+
+
+# --------------------------------------------------------------------------
+# staged ops
+# --------------------------------------------------------------------------
+def crosswise_diffs(data, nn_data, data_idx, nn_idx) -> torch.Tensor:
+    lib = L.lib()
+    data, nn_data = as_2d(fdev(data)), as_2d(fdev(nn_data))
+    nn_idx = idev(nn_idx)
+    data_idx = None if data_idx is None else idev(data_idx)
+    b, k = nn_idx.shape
+    d = data.shape[1]
+    out = torch.empty((b, k, d), dtype=f64, device=data.device)
+    L.check(lib.mgp_crosswise_diffs(_p(data), _p(nn_data), _p(data_idx), _p(nn_idx), b, k, d,
+                                    _p(out), _stream()))
+    return out
+
+
+def pairwise_diffs(data, nn_idx) -> torch.Tensor:
+    lib = L.lib()
+    data = as_2d(fdev(data))
+    nn_idx = idev(nn_idx)
+    b, k = nn_idx.shape
+    d = data.shape[1]
+    out = torch.empty((b, k, k, d), dtype=f64, device=data.device)
+    L.check(lib.mgp_pairwise_diffs(_p(data), _p(nn_idx), b, k, d, _p(out), _stream()))
+    return out
+
+
+def metric_reduce(metric_id, diffs, length_scale=None) -> torch.Tensor:
+    lib = L.lib()
+    diffs = fdev(diffs, "diffs")
+    d = diffs.shape[-1]
+    rows = diffs.numel() // d if d else 0
+    out = torch.empty(diffs.shape[:-1], dtype=f64, device=diffs.device)
+    ls_host = None
+    if length_scale is not None:
+        ls = _ls_list(length_scale)
+        if len(ls) != d:
+            raise ValueError(
+                f"Difference tensor of shape {tuple(diffs.shape)} must have final dimension "
+                f"size of {len(ls)}"
+            )
+        ls_host = C.cast(_host_doubles(ls), C.POINTER(C.c_double))
+    L.check(lib.mgp_metric_reduce(int(metric_id), _p(diffs), rows, d, ls_host, _p(out),
+                                  _stream()))
+    return out
+
+
+def crosswise_dists(metric_id, data, nn_data, data_idx, nn_idx) -> torch.Tensor:
+    lib = L.lib()
+    data, nn_data = as_2d(fdev(data)), as_2d(fdev(nn_data))
+    nn_idx = idev(nn_idx)
+    data_idx = None if data_idx is None else idev(data_idx)
+    b, k = nn_idx.shape
+    out = torch.empty((b, k), dtype=f64, device=data.device)
+    L.check(lib.mgp_crosswise_dists(int(metric_id), _p(data), _p(nn_data), _p(data_idx),
+                                    _p(nn_idx), b, k, data.shape[1], _p(out), _stream()))
+    return out
+
+
+def pairwise_dists(metric_id, data, nn_idx) -> torch.Tensor:
+    lib = L.lib()
+    data = as_2d(fdev(data))
+    nn_idx = idev(nn_idx)
+    b, k = nn_idx.shape
+    out = torch.empty((b, k, k), dtype=f64, device=data.device)
+    L.check(lib.mgp_pairwise_dists(int(metric_id), _p(data), _p(nn_idx), b, k, data.shape[1],
+                                   _p(out), _stream()))
+    return out
+
+
+def kernel_apply(kernel_id, x, pre_scale=1.0) -> torch.Tensor:
+    lib = L.lib()
+    x = fdev(x, "dists")
+    out = torch.empty_like(x)
+    L.check(lib.mgp_kernel_apply(int(kernel_id), _p(x), float(pre_scale), x.numel(), _p(out),
+                                 _stream()))
+    return out
+
+
+def perturb(Kin, noise) -> torch.Tensor:
+    lib = L.lib()
+    Kin = fdev(Kin, "Kin")
+    if Kin.dim() != 3 or Kin.shape[1] != Kin.shape[2]:
+        raise ValueError(
+            f"homoscedastic perturbation is not implemented for tensors of shape "
+            f"{tuple(Kin.shape)}"
+        )
+    b, k, _ = Kin.shape
+    out = torch.empty_like(Kin)
+    noise_bk = None
+    noise_val = 0.0
+    if isinstance(noise, torch.Tensor) and noise.dim() > 0:
+        noise_bk = fdev(noise).reshape(b, k).contiguous()
+    else:
+        noise_val = float(noise)
+    L.check(lib.mgp_perturb(_p(Kin), b, k, noise_val, _p(noise_bk), _p(out), _stream()))
+    return out
+
+
+def solve(Kin, Kcross=None, Y=None, kout=1.0, *, want_mean=False, want_var=False,
+          want_yky=False, want_coeffs=False):
+    """Batched SPD solve on materialised tensors (K5).  Y is (b,k) or (b,k,r)."""
+    lib = L.lib()
+    Kin = fdev(Kin, "Kin")
+    if Kin.dim() != 3 or Kin.shape[1] != Kin.shape[2]:
+        raise ValueError(f"Kin must be (batch_count, nn_count, nn_count), not {tuple(Kin.shape)}")
+    b, k, _ = Kin.shape
+    dev = Kin.device
+    r = 0
+    if Kcross is not None:
+        Kcross = fdev(Kcross, "Kcross").reshape(b, k).contiguous()
+    if Y is not None:
+        Y = fdev(Y, "nn_targets")
+        Y = Y.reshape(b, k, -1).contiguous()
+        r = Y.shape[2]
+    out = {}
+    if want_mean:
+        out["mean"] = torch.empty((b, r), dtype=f64, device=dev)
+    if want_var:
+        out["var"] = torch.empty((b,), dtype=f64, device=dev)
+    if want_yky:
+        out["yky"] = torch.empty((b,), dtype=f64, device=dev)
+    if want_coeffs:
+        out["coeffs"] = torch.empty((b, k, r), dtype=f64, device=dev)
+    ws_bytes = lib.mgp_solve_workspace_bytes(b, k, r)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+    L.check(lib.mgp_solve(_p(Kin), _p(Kcross), _p(Y), b, k, r, float(kout), _p(out.get("mean")),
+                          _p(out.get("var")), _p(out.get("yky")), _p(out.get("coeffs")), None,
+                          _p(ws), ws_bytes, _stream()))
+    return out
+
+
+def rowdot(Kcross, coeffs) -> torch.Tensor:
+    lib = L.lib()
+    Kcross = fdev(Kcross, "Kcross")
+    coeffs = fdev(coeffs, "coeffs_tensor")
+    b, k = Kcross.shape
+    coeffs = coeffs.reshape(b, k, -1).contiguous()
+    r = coeffs.shape[2]
+    out = torch.empty((b, r), dtype=f64, device=Kcross.device)
+    L.check(lib.mgp_rowdot(_p(Kcross), _p(coeffs), b, k, r, _p(out), _stream()))
+    return out
+
+
+def fp64_probe(mode: int, blocks: int, threads: int, iters: int) -> torch.Tensor:
+    lib = L.lib()
+    sink = torch.empty((blocks * threads,), dtype=f64, device="cuda")
+    L.check(lib.mgp_fp64_probe(mode, blocks, threads, iters, _p(sink), _stream()))
+    return sink

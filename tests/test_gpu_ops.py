@@ -1,0 +1,234 @@
+"""GPU parity: every C-ABI entry point against the numpy oracle (and through it
+the reference's recorded outputs) on the seeded cases of oracle/cases.py.
+
+Tolerance (north_star): |a-b| <= 1e-10 * max(|b|, ||b||_inf) in fp64; index
+arrays bit-exact."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_oracle as O
+from oracle.cases import CASES, make_data
+
+from conftest import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+def _ls(case, f=1.0):
+    return (np.asarray(case.length_scale) * f) if case.anisotropic else case.length_scale * f
+
+
+def _2d(x):
+    return x[:, None] if x.ndim == 1 else x
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from muygpys_b200 import ops as _ops
+
+    return _ops
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_fused_predict_matches_reference(ops, case):
+    g = load_golden(case.name)
+    data = make_data(case)
+    nn = g["test_nn_idx"]
+    y = data["train_y"]
+    noise = dev(data["hetero_train_noise"][nn]) if case.hetero else case.noise
+    out = ops.fused_posterior(dev(data["train_x"]), dev(data["test_x"]), None, dev(nn), dev(y),
+                              kernel_id=case.kernel_id, metric_id=case.metric_id,
+                              length_scale=_ls(case), noise=noise, scale=float(g["scale_val"]),
+                              want_status=True)
+    mean = out["mean"].cpu().numpy()
+    if case.r == 1:
+        mean = mean[:, 0]
+    assert int(out["status"].sum()) == 0
+    assert_close(mean, g["mean"], RTOL, "mean vs reference")
+    assert_close(out["var"].cpu().numpy(), g["var"], RTOL, "var vs reference")
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.batch and c.r == 1],
+                         ids=lambda c: c.name)
+def test_fused_train_batch_yky_and_query_idx(ops, case):
+    g = load_golden(case.name)
+    data = make_data(case)
+    x = _2d(data["train_x"])
+    y = data["train_y"][:, 0]
+    bi, bnn = data["batch_idx"], g["batch_nn_idx"]
+    out = ops.fused_posterior(dev(x), dev(x), dev(bi), dev(bnn), dev(y),
+                              kernel_id=case.kernel_id, metric_id=case.metric_id,
+                              length_scale=_ls(case), noise=case.noise, want_yky=True)
+    Kin, Kcross = O.kernel_tensors(case.kernel_id, case.metric_id, _ls(case), x, x, bi, bnn)
+    pK = O.homoscedastic_perturb(Kin, case.noise)
+    assert_close(out["mean"].cpu().numpy()[:, 0], O.posterior_mean(pK, Kcross, y[bnn]), RTOL)
+    assert_close(out["var"].cpu().numpy(), O.diagonal_variance(pK, Kcross), RTOL)
+    yky = out["yky"].cpu().numpy()
+    want = np.einsum("bi,bi->b", y[bnn], np.linalg.solve(pK, y[bnn][..., None])[..., 0])
+    assert_close(yky, want, RTOL, "yky")
+    assert_close(yky.sum() / (len(bi) * case.k), g["analytic_scale"], RTOL, "analytic scale")
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.fast], ids=lambda c: c.name)
+def test_fused_coeffs_and_fast_mean(ops, case):
+    g = load_golden(case.name)
+    data = make_data(case)
+    x, tx = _2d(data["train_x"]), _2d(data["test_x"])
+    y = data["train_y"]
+    tr_nn, _ = O.knn_exact(x, x, case.k)
+    fast_nn = O.fast_nn_update(tr_nn)
+    closest = g["test_nn_idx"][:, 0]
+    # precompute for every training point, like the reference workflow
+    out = ops.fused_posterior(dev(x), dev(x), None, dev(fast_nn), dev(y),
+                              kernel_id=case.kernel_id, metric_id=case.metric_id,
+                              length_scale=_ls(case), noise=case.noise, want_mean=False,
+                              want_var=False, want_coeffs=True)
+    coeffs = out["coeffs"]
+    got = coeffs.cpu().numpy()
+    if case.r == 1:
+        got = got[:, :, 0]
+    assert_close(got[:64], g["fast_coeffs_head"], 1e-9, "coeffs head")
+    assert_close(got[closest], g["fast_coeffs_closest"], 1e-9, "coeffs[closest]")
+    fm = ops.fast_mean(dev(x), dev(tx), None, dev(fast_nn[closest]), dev(closest), coeffs,
+                       kernel_id=case.kernel_id, metric_id=case.metric_id,
+                       length_scale=_ls(case)).cpu().numpy()
+    if case.r == 1:
+        fm = fm[:, 0]
+    assert_close(fm, g["fast_mean"], RTOL, "fast mean")
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_knn_bit_exact(ops, case):
+    g = load_golden(case.name)
+    data = make_data(case)
+    idx, d2 = ops.knn(dev(data["train_x"]), dev(data["test_x"]), case.k)
+    assert idx.dtype == torch.int64
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["test_nn_idx"])
+    assert_close(d2.cpu().numpy(), g["test_nn_d2"], 1e-12, "dist2")
+    if case.batch:
+        x = dev(_2d(data["train_x"]))
+        bi = dev(data["batch_idx"])
+        # reference semantics: query k+1, drop column 0 (S/neighbors.py:207-211)
+        idx1, d21 = ops.knn(x, x[bi], case.k + 1)
+        np.testing.assert_array_equal(idx1[:, 1:].cpu().numpy(), g["batch_nn_idx"])
+        # explicit self exclusion gives the same rows when points are distinct
+        idx2, d22 = ops.knn(x, x[bi], case.k, self_idx=bi)
+        np.testing.assert_array_equal(idx2.cpu().numpy(), g["batch_nn_idx"])
+        assert_close(d22.cpu().numpy(), g["batch_nn_d2"], 1e-12)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_staged_ops(ops, case):
+    g = load_golden(case.name)
+    data = make_data(case)
+    rows = g["stage_Kin"].shape[0]
+    nn = g["test_nn_idx"][:rows]
+    x, tx = dev(data["train_x"]), dev(data["test_x"])
+    ar = dev(np.arange(rows))
+    cd = ops.crosswise_diffs(tx, x, ar, dev(nn))
+    pd = ops.pairwise_diffs(x, dev(nn))
+    np.testing.assert_array_equal(
+        cd.cpu().numpy(), O.crosswise_tensor(data["test_x"], data["train_x"], np.arange(rows), nn))
+    np.testing.assert_array_equal(pd.cpu().numpy(), O.pairwise_tensor(data["train_x"], nn))
+    if case.anisotropic:
+        xc = ops.metric_reduce(case.metric_id, cd, length_scale=_ls(case))
+        xp = ops.metric_reduce(case.metric_id, pd, length_scale=_ls(case))
+        pre = 1.0
+    else:
+        xc = ops.crosswise_dists(case.metric_id, tx, x, ar, dev(nn))
+        xp = ops.pairwise_dists(case.metric_id, x, dev(nn))
+        assert_close(xc.cpu().numpy(), g["stage_crosswise"], 1e-14)
+        assert_close(xp.cpu().numpy(), g["stage_pairwise"], 1e-14)
+        assert_close(ops.metric_reduce(case.metric_id, cd).cpu().numpy(), g["stage_crosswise"],
+                     1e-14)
+        ls = case.length_scale
+        pre = 1.0 / ls if case.metric_id == O.METRIC_L2 else 1.0 / ls**2
+    Kin = ops.kernel_apply(case.kernel_id, xp, pre)
+    Kcross = ops.kernel_apply(case.kernel_id, xc, pre)
+    assert_close(Kin.cpu().numpy(), g["stage_Kin"], 1e-13, "Kin")
+    assert_close(Kcross.cpu().numpy(), g["stage_Kcross"], 1e-13, "Kcross")
+    # perturb + solve on the reference's own tensors
+    Kin_ref, Kcross_ref, Y = g["stage_Kin"], g["stage_Kcross"], g["stage_nn_targets"]
+    if case.hetero:
+        nz = data["hetero_train_noise"][nn]
+        pK = ops.perturb(dev(Kin_ref), dev(nz))
+        want_pK = O.heteroscedastic_perturb(Kin_ref, nz)
+    else:
+        pK = ops.perturb(dev(Kin_ref), case.noise)
+        want_pK = O.homoscedastic_perturb(Kin_ref, case.noise)
+    np.testing.assert_array_equal(pK.cpu().numpy(), want_pK)
+    out = ops.solve(pK, dev(Kcross_ref), dev(Y), 1.0, want_mean=True, want_var=True,
+                    want_yky=True, want_coeffs=True)
+    mean = out["mean"].cpu().numpy().reshape(Y.shape[:1] + Y.shape[2:])
+    assert_close(mean, O.posterior_mean(want_pK, Kcross_ref, Y), RTOL, "staged mean")
+    assert_close(out["var"].cpu().numpy(), O.diagonal_variance(want_pK, Kcross_ref), RTOL)
+    assert_close(out["yky"].cpu().numpy().sum(), O.analytic_scale_unnormalized(want_pK, Y), RTOL)
+    coeffs = O.fast_precompute(want_pK, Y)
+    assert_close(out["coeffs"].cpu().numpy().reshape(coeffs.shape), coeffs, 1e-9, "coeffs")
+    fm = ops.rowdot(dev(Kcross_ref), out["coeffs"]).cpu().numpy()
+    assert_close(fm.reshape(mean.shape), O.fast_posterior_mean(Kcross_ref, coeffs), 1e-9)
+
+
+def test_losses(ops):
+    g = load_golden("losses")
+    from muygpys_b200 import _lib as L
+
+    for r in (1, 2, 10):
+        p, t, v = dev(g[f"pred_r{r}"]), dev(g[f"targ_r{r}"]), dev(g[f"var_r{r}"])
+        P = ops.loss_partials(L.LOSS_MSE, p, t).cpu().numpy()
+        assert_close(P[L.P_SQERR] / P[L.P_COUNT], g[f"mse_r{r}"], 1e-13)
+        assert P[L.P_ROWS] == p.shape[0]
+        P = ops.loss_partials(L.LOSS_PSEUDO_HUBER, p, t, boundary_scale=1.5).cpu().numpy()
+        assert_close(P[L.P_AUX], g[f"phuber_r{r}"], 1e-13)
+        P = ops.loss_partials(L.LOSS_PSEUDO_HUBER, p, t, boundary_scale=2.5).cpu().numpy()
+        assert_close(P[L.P_AUX], g[f"phuber25_r{r}"], 1e-13)
+        if r == 1:
+            s = dev(np.array([1.3]))
+            P = ops.loss_partials(L.LOSS_LOOL, p, t, var=v, scale_dev=s).cpu().numpy()
+            assert_close(P[L.P_AUX], g["lool_r1"], 1e-13)
+            # single-allreduce form: sum e^2/v / s + sum log v + b log s
+            alt = P[L.P_SQERR_V] / 1.3 + P[L.P_LOGV] + P[L.P_ROWS] * np.log(1.3)
+            assert_close(alt, g["lool_r1"], 1e-13)
+            P = ops.loss_partials(L.LOSS_LOOPH, p, t, var=v, scale_dev=s,
+                                  boundary_scale=3.0).cpu().numpy()
+            assert_close(P[L.P_AUX], g["looph_r1"], 1e-13)
+            P = ops.loss_partials(L.LOSS_LOOPH, p, t, var=v, scale_dev=dev(np.array([0.7])),
+                                  boundary_scale=2.0).cpu().numpy()
+            assert_close(P[L.P_AUX], g["looph2_r1"], 1e-13)
+        else:
+            oh = dev(g[f"onehot_r{r}"])
+            P = ops.loss_partials(L.LOSS_CROSS_ENTROPY, p, oh).cpu().numpy()
+            assert_close(P[L.P_AUX], g[f"ce_r{r}"], 1e-13)
+            P = ops.loss_partials(L.LOSS_CROSS_ENTROPY, p * 60.0, oh).cpu().numpy()
+            assert_close(P[L.P_AUX], g[f"ce_big_r{r}"], 1e-13)
+
+
+def test_error_behaviour(ops):
+    x = torch.rand(50, 2, dtype=torch.float64, device="cuda")
+    y = torch.rand(50, dtype=torch.float64, device="cuda")
+    nn = torch.randint(0, 50, (4, 5), device="cuda")
+    with pytest.raises(ValueError):  # anisotropic length-scale count mismatch
+        ops.fused_posterior(x, x, None, nn, y, kernel_id=2, metric_id=0,
+                            length_scale=[0.1, 0.2, 0.3])
+    with pytest.raises(ValueError):
+        ops.fused_posterior(x, x, None, nn, y, kernel_id=9, metric_id=0, length_scale=0.1)
+    with pytest.raises(Exception):
+        ops.fused_posterior(x.cpu(), x, None, nn, y, kernel_id=2, metric_id=0, length_scale=0.1)
+    with pytest.raises(ValueError):
+        ops.perturb(torch.rand(3, 4, dtype=torch.float64, device="cuda"), 1e-3)
+    # empty batch is a no-op
+    out = ops.fused_posterior(x, x, None, nn[:0], y, kernel_id=2, metric_id=0, length_scale=0.1)
+    assert out["mean"].shape == (0, 1) and out["var"].shape == (0,)
+    # non-SPD neighbourhood (duplicate rows, zero nugget) is flagged, not fatal
+    dup = torch.zeros((1, 5), dtype=torch.int64, device="cuda")
+    out = ops.fused_posterior(x, x, None, dup, y, kernel_id=2, metric_id=0, length_scale=0.1,
+                              noise=0.0, want_status=True)
+    assert int(out["status"][0]) == 1 and torch.isnan(out["var"][0])
