@@ -124,6 +124,11 @@ const char* mgp_last_error(void);
 size_t mgp_fused_workspace_bytes(const mgp_problem* p);
 int mgp_fused_posterior(const mgp_problem* p, void* ws, size_t ws_bytes, void* stream);
 
+/* Test/bench hook: 0 = choose automatically, 1 = always the generic shared-memory
+ * kernel, 2 = the register-tile DMMA kernel where supported.  Lets the two
+ * independently written variants be cross-checked on identical inputs. */
+int mgp_set_fused_variant(int32_t variant);
+
 /* ---- losses and scale partials (a14/a15) -------------------------------
  * Accumulates (adds) a partials record over b rows into `partials`
  * (MGP_PARTIALS doubles, zero it first).  `var`/`yky` may be NULL when the loss

@@ -1,23 +1,482 @@
-// K1 (tile variant) -- placeholder until the register-resident DMMA kernel lands.
+// K1 (tile variant) -- the fast path of the fused neighbourhood kernel.
+//
+// One WARP owns one neighbourhood.  The augmented matrix (nbhd_smem.cuh) is cut
+// into 8x8 tiles; its lower triangle lives in REGISTERS as mma.sync.m8n8k4.f64
+// fragments and is factorised tile column by tile column (left-looking):
+//
+//   for each tile column J:
+//     N[I][J] (+)= L[I][P] * L[J][P]^T  for all finished P < J   -- FP64 DMMA
+//     C = -N ; in-tile Cholesky of C[J][J] and triangular solve of the tiles
+//     below it, 8 columns, lane-parallel with quad/warp shuffles
+//     re-layout C[I][J] (accumulator layout) -> A/B fragment layout for later J
+//
+// tcgen05 has no FP64 type, so on sm_100a the FP64 tensor path is mma.sync DMMA;
+// measured on B200 it issues at the same 64 FMA/clk/SM as DFMA (tools/fp64_probe.py)
+// but needs 1/8 of the issue slots and no operand traffic, which is what lets
+// the shuffles, selects and address arithmetic of the other phases overlap.
+//
+// Assembly phase: the k(k+1)/2 + k covariances are evaluated in a flat,
+// perfectly balanced loop (1 element per lane per iteration, (i,j) from a
+// shared-memory table) with hand-rolled exp / sqrt that cost 9 / 5 FP64 issue
+// slots instead of libm's ~17 / ~8, and scattered (negated) into the tile
+// layout in shared memory, from where each tile column is picked up with one
+// LDS.128 per lane per tile.
+//
+// Supported shapes: roundup8(roundup4(k) + 1 + r) <= 56 (one warp's registers),
+// d <= 8.  Everything else takes the generic shared-memory kernel.
 #include "common.cuh"
 
 namespace mgp {
 
+namespace {
+
+constexpr int TILE_WARPS = 4;        // warps (neighbourhoods in flight) per CTA
+constexpr int TILE_MAX_D = 8;
+constexpr int EXP_TABLE = 64;
+
+__constant__ double c_exp_tab[EXP_TABLE];  // 2^(j/64), correctly rounded on the host
+
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+
+__device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double rsqrt_seed(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RSQ64H, ~20 bits
+  return r;
+}
+
+// 1/sqrt(p), one third-order step from the 20-bit seed (error ~ 2^-62)
+__device__ __forceinline__ double rsqrt_fast(double p) {
+  const double r = rsqrt_seed(p);
+  const double t = p * r;
+  const double e = fma(-t, r, 1.0);
+  const double v = e * fma(e, 0.375, 0.5);
+  return fma(r, v, r);
+}
+
+// sqrt(x) for x >= 0 (0 -> 0)
+__device__ __forceinline__ double sqrt_fast(double x) {
+  const double r = rsqrt_seed(x);
+  const double g = x * r;
+  const double e = fma(-g, r, 1.0);
+  const double v = e * fma(e, 0.375, 0.5);
+  const double s = fma(g, v, g);
+  return (x > 1e-290) ? s : 0.0;
+}
+
+// exp(-s), s >= 0: 64-entry table of 2^(j/64) + degree-5 polynomial.
+// |abs error| <= ~2.3e-16 (validated against long double on the host).
+__device__ __forceinline__ double exp_neg(double s, const double* __restrict__ tab64) {
+  const double LOG2E = 1.4426950408889634;
+  const double MAGIC = 105553116266496.0;  // 1.5 * 2^46: ulp = 2^-6
+  const double t = fma(s, -LOG2E, MAGIC);
+  const int ki = __double2loint(t);
+  const double tr = t - MAGIC;
+  const double g = fma(s, -LOG2E, -tr);
+  double p = 0.0013333558146428443;
+  p = fma(g, p, 0.009618129107628477);
+  p = fma(g, p, 0.05550410866482158);
+  p = fma(g, p, 0.2402265069591007);
+  p = fma(g, p, 0.6931471805599453);
+  p = fma(g, p, 1.0);
+  const double res = tab64[ki & (EXP_TABLE - 1)] * p;
+  const int n = ki >> 6;
+  const double out = __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
+  return (s < 700.0) ? out : 0.0;
+}
+
+struct TileArgs {
+  const double* train_x;
+  const double* query_x;
+  const int64_t* query_idx;
+  const int64_t* nn_idx;
+  const double* train_y;
+  const double* noise_bk;
+  double* mean;
+  double* var;
+  double* yky;
+  double* coeffs;
+  int32_t* status;
+  long long b;
+  int k, kp, d, r;
+  int n_elem;      // k(k+1)/2 + k table entries
+  double noise, scale;
+  int kernel_id, metric_id;
+  double coord_scale[TILE_MAX_D];  // per-feature multiplier folded into staged coordinates
+  double post_scale;               // F2 metric with Matern: s = post_scale * u2
+};
+
+// covariance from u2 = sum of squared prescaled differences
+__device__ __forceinline__ double cov_from_u2(const TileArgs& a, double u2, const double* tab64) {
+  if (a.metric_id == MGP_METRIC_L2) {
+    switch (a.kernel_id) {
+      case MGP_KERNEL_MATERN_05:
+        return exp_neg(sqrt_fast(u2), tab64);
+      case MGP_KERNEL_MATERN_15: {
+        const double s = sqrt_fast(u2);
+        return (1.0 + s) * exp_neg(s, tab64);
+      }
+      case MGP_KERNEL_MATERN_25: {
+        const double s = sqrt_fast(u2);
+        return fma(u2, 1.0 / 3.0, 1.0 + s) * exp_neg(s, tab64);
+      }
+      case MGP_KERNEL_MATERN_INF:
+        return exp_neg(0.5 * u2, tab64);
+      default:  // RBF fed with l2 distances: exp(-x/2)
+        return exp_neg(0.5 * sqrt_fast(u2), tab64);
+    }
+  }
+  const double s = a.post_scale * u2;  // F2: the kernel argument is the squared form
+  switch (a.kernel_id) {
+    case MGP_KERNEL_RBF:
+      return exp_neg(0.5 * s, tab64);
+    case MGP_KERNEL_MATERN_05:
+      return exp_neg(s, tab64);
+    case MGP_KERNEL_MATERN_15:
+      return (1.0 + s) * exp_neg(s, tab64);
+    case MGP_KERNEL_MATERN_25:
+      return fma(s * s, 1.0 / 3.0, 1.0 + s) * exp_neg(s, tab64);
+    default:
+      return exp_neg(0.5 * s * s, tab64);
+  }
+}
+
+__device__ __forceinline__ int tile_base(int I, int J) { return ((I * (I + 1)) / 2 + J) * 64; }
+
+template <int T>
+__global__ void __launch_bounds__(TILE_WARPS * 32, 3)
+    fused_tile_kernel(const TileArgs a, size_t warp_doubles) {
+  extern __shared__ double smem[];
+  constexpr int NT = T * (T + 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rho = lane >> 2, q = lane & 3;
+  const int k = a.k, kp = a.kp, d = a.d, r = a.r;
+
+  // CTA-shared: exp table and the (tile row, column) table of the flat element list
+  double* tab64 = smem;
+  unsigned short* etab = (unsigned short*)(tab64 + EXP_TABLE);
+  const int etab_doubles = (((a.n_elem + 3) / 4) + 1) & ~1;
+  double* wbase = tab64 + EXP_TABLE + etab_doubles + (size_t)warp * warp_doubles;
+  double* tiles = wbase;               // NT * 64 doubles, tile-major, row-major inside
+  double* pts = tiles + NT * 64;       // (k+1) x d prescaled coordinates, row k = query
+
+  for (int j = threadIdx.x; j < EXP_TABLE; j += blockDim.x) tab64[j] = c_exp_tab[j];
+  for (int e = threadIdx.x; e < a.n_elem; e += blockDim.x) {
+    // e < k(k+1)/2: lower triangle in row-major order; then the k cross entries
+    const int tri = k * (k + 1) / 2;
+    int ti, j;
+    if (e < tri) {
+      int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      while (i * (i + 1) / 2 > e) --i;
+      ti = i;
+      j = e - i * (i + 1) / 2;
+    } else {
+      ti = kp;
+      j = e - tri;
+    }
+    etab[e] = (unsigned short)((ti << 8) | j);
+  }
+  __syncthreads();
+
+  const long long wglobal = (long long)blockIdx.x * TILE_WARPS + warp;
+  const long long wstride = (long long)gridDim.x * TILE_WARPS;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+
+  for (long long row = wglobal; row < a.b; row += wstride) {
+    // ---- zero the tile image, stage coordinates and targets ----------------
+    for (int e = lane; e < NT * 32; e += 32) reinterpret_cast<double2*>(tiles)[e] = make_double2(0.0, 0.0);
+    __syncwarp();
+    const long long qrow = a.query_idx ? a.query_idx[row] : row;
+    for (int i = lane; i <= k; i += 32) {
+      const bool is_q = (i == k);
+      const long long src = is_q ? qrow : a.nn_idx[row * k + i];
+      const double* px = (is_q ? a.query_x : a.train_x) + src * d;
+      for (int f = 0; f < d; ++f) pts[i * d + f] = px[f] * a.coord_scale[f];
+      if (!is_q && a.train_y) {
+        for (int c = 0; c < r; ++c) {  // augmented rows kp+1+c hold -y (tiles hold N = -A)
+          const int ti = kp + 1 + c;
+          tiles[tile_base(ti >> 3, i >> 3) + (ti & 7) * 8 + (i & 7)] = -a.train_y[src * r + c];
+        }
+      }
+    }
+    // identity padding rows k..kp-1 and Kout = 1 at (kp,kp)
+    if (lane <= kp - k) {
+      const int i = k + lane;
+      tiles[tile_base(i >> 3, i >> 3) + (i & 7) * 9] = -1.0;
+    }
+    __syncwarp();
+
+    // ---- covariance assembly: flat balanced loop ---------------------------
+    for (int e = lane; e < a.n_elem; e += 32) {
+      const int packed = etab[e];
+      const int ti = packed >> 8, j = packed & 255;
+      const int pi = (ti == kp) ? k : ti;
+      double u2 = 0.0;
+      for (int f = 0; f < d; ++f) {
+        const double df = pts[pi * d + f] - pts[j * d + f];
+        u2 = fma(df, df, u2);
+      }
+      double v = cov_from_u2(a, u2, tab64);
+      if (ti == j) v += a.noise_bk ? a.noise_bk[row * k + j] : a.noise;
+      tiles[tile_base(ti >> 3, j >> 3) + (ti & 7) * 8 + (j & 7)] = -v;
+    }
+    __syncwarp();
+
+    // ---- left-looking tiled Cholesky in registers ---------------------------
+    double la_lo[T][T], la_hi[T][T];  // [I][P], I > P: finished tiles as A/B fragments
+    bool ok = true;
+#pragma unroll
+    for (int J = 0; J < T; ++J) {
+      double c[T][2];
+#pragma unroll
+      for (int I = J; I < T; ++I) {
+        const double2 v = *reinterpret_cast<const double2*>(tiles + tile_base(I, J) + rho * 8 + 2 * q);
+        c[I][0] = v.x;
+        c[I][1] = v.y;
+      }
+#pragma unroll
+      for (int P = 0; P < J; ++P) {
+        if (8 * P < kp) {  // tile column P carries eliminated columns
+          // half-eliminated tile column (kp % 8 == 4): only its first 4 columns are L
+          const bool full = (8 * P + 8 <= kp);
+#pragma unroll
+          for (int I = J; I < T; ++I) {
+            // the B fragment of tile (J,P) equals its A fragment (see header comment)
+            dmma_acc(c[I][0], c[I][1], la_lo[I][P], la_lo[J][P]);
+            if (full) dmma_acc(c[I][0], c[I][1], la_hi[I][P], la_hi[J][P]);
+          }
+        }
+      }
+#pragma unroll
+      for (int I = J; I < T; ++I) {
+        c[I][0] = -c[I][0];
+        c[I][1] = -c[I][1];
+      }
+      const int ncols = min(8, kp - 8 * J);  // eliminated columns in this tile column
+      if (ncols > 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < ncols) {
+            const int qj = j >> 1, bj = j & 1;
+            const double p = shfl_d(c[J][bj], j * 4 + qj);
+            ok = ok && (p > 0.0);
+            const double rinv = rsqrt_fast(p);
+#pragma unroll
+            for (int I = J; I < T; ++I)
+              if (q == qj) c[I][bj] *= rinv;
+            double lc0 = shfl_d(c[J][bj], (2 * q) * 4 + qj);
+            double lc1 = shfl_d(c[J][bj], (2 * q + 1) * 4 + qj);
+            lc0 = (2 * q > j) ? lc0 : 0.0;
+            lc1 = (2 * q + 1 > j) ? lc1 : 0.0;
+#pragma unroll
+            for (int I = J; I < T; ++I) {
+              const double lr = shfl_d(c[I][bj], (lane & ~3) | qj);
+              if (j < 6) c[I][0] = fma(-lr, lc0, c[I][0]);
+              if (j < 7) c[I][1] = fma(-lr, lc1, c[I][1]);
+            }
+          }
+        }
+        // re-layout the finished tiles below the diagonal into A/B fragments
+        if (J + 1 < T) {
+          const int kap = q;  // fragment column this lane owns
+#pragma unroll
+          for (int I = J + 1; I < T; ++I) {
+            // quad permutation {0,1},{2,3},{4,5},{6,7} -> {0,4},{1,5},{2,6},{3,7} in 2 rounds
+            const int qb = lane & ~3;
+            // round A: lanes present L0:c1 L1:c0 L2:c0 L3:c0 ; readers L1<-L0 L2<-L1 L0<-L2
+            const double presA = (q == 0) ? c[I][1] : c[I][0];
+            const int srcA = qb | ((q == 1) ? 0 : (q == 2) ? 1 : (q == 0) ? 2 : 3);
+            const double gotA = shfl_d(presA, srcA);
+            // round B: L1:c1 L2:c1 L3:c0 ; readers L3<-L1 L1<-L2 L2<-L3
+            const double presB = (q == 3) ? c[I][0] : c[I][1];
+            const int srcB = qb | ((q == 3) ? 1 : (q == 1) ? 2 : (q == 2) ? 3 : 0);
+            const double gotB = shfl_d(presB, srcB);
+            // lane kap needs cols kap (lo) and 4+kap (hi)
+            double lo, hi;
+            if (kap == 0) {
+              lo = c[I][0];  // col 0 (own)
+              hi = gotA;     // col 4 from L2
+            } else if (kap == 1) {
+              lo = gotA;     // col 1 from L0
+              hi = gotB;     // col 5 from L2
+            } else if (kap == 2) {
+              lo = gotA;     // col 2 from L1
+              hi = gotB;     // col 6 from L3
+            } else {
+              lo = gotB;     // col 3 from L1
+              hi = c[I][1];  // col 7 (own)
+            }
+            la_lo[I][J] = lo;
+            la_hi[I][J] = hi;
+          }
+        }
+      }
+      // write back what later phases read from shared memory
+      if (a.coeffs || 8 * J + 8 > kp) {
+#pragma unroll
+        for (int I = J; I < T; ++I)
+          *reinterpret_cast<double2*>(tiles + tile_base(I, J) + rho * 8 + 2 * q) =
+              make_double2(c[I][0], c[I][1]);
+      }
+    }
+    __syncwarp();
+
+    // ---- outputs from the Schur complement ----------------------------------
+    auto elem = [&](int i, int j) -> double {
+      return tiles[tile_base(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7)];
+    };
+    if (lane == 0) {
+      if (a.var) a.var[row] = ok ? a.scale * elem(kp, kp) : nan;
+      if (a.status) a.status[row] = ok ? 0 : 1;
+      if (a.yky) {
+        double s = 0.0;
+        for (int c2 = 0; c2 < r; ++c2) s -= elem(kp + 1 + c2, kp + 1 + c2);
+        a.yky[row] = ok ? s : nan;
+      }
+    }
+    if (a.mean)
+      for (int c2 = lane; c2 < r; c2 += 32) a.mean[row * r + c2] = ok ? -elem(kp + 1 + c2, kp) : nan;
+    if (a.coeffs) {
+      // back substitution L^T C = U on the tile image (rows kp+1+c hold U^T)
+      for (int i = k - 1; i >= 0; --i) {
+        const double inv = 1.0 / elem(i, i);
+        __syncwarp();
+        for (int c2 = lane; c2 < r; c2 += 32) {
+          const int ti = kp + 1 + c2;
+          tiles[tile_base(ti >> 3, i >> 3) + (ti & 7) * 8 + (i & 7)] *= inv;
+        }
+        __syncwarp();
+        for (int e = lane; e < r * i; e += 32) {
+          const int c2 = e / i, j = e - c2 * i;
+          const int ti = kp + 1 + c2;
+          double* dst = &tiles[tile_base(ti >> 3, j >> 3) + (ti & 7) * 8 + (j & 7)];
+          *dst = fma(-elem(ti, i), elem(i, j), *dst);
+        }
+        __syncwarp();
+      }
+      for (int e = lane; e < k * r; e += 32) {
+        const int j = e / r, c2 = e - j * r;
+        a.coeffs[(row * k + j) * r + c2] = ok ? elem(kp + 1 + c2, j) : nan;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+static int tiles_needed(int k, int r) {
+  const int kp = (k + 3) & ~3;
+  return (kp + 1 + r + 7) / 8;
+}
+
+}  // namespace
+
+static int g_variant = 0;  // 0 auto, 1 force generic, 2 force tile (error if unsupported)
+
 int fused_tile_supported(const mgp_problem* p, const Model& model) {
-  (void)p;
   (void)model;
-  return 0;
+  if (g_variant == 1) return 0;
+  if (p->d > TILE_MAX_D) return 0;
+  if (p->k > 255) return 0;
+  return tiles_needed(p->k, p->r) <= 7;
 }
 
 int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t ws_bytes,
                       cudaStream_t stream) {
-  (void)p;
-  (void)model;
   (void)ws;
   (void)ws_bytes;
-  (void)stream;
-  set_error("tile variant not built");
-  return MGP_ERR_UNSUPPORTED;
+  static bool table_ready = false;
+  if (!table_ready) {
+    double host_tab[EXP_TABLE];
+    for (int j = 0; j < EXP_TABLE; ++j) host_tab[j] = (double)exp2l((long double)j / EXP_TABLE);
+    cudaError_t e = cudaMemcpyToSymbol(c_exp_tab, host_tab, sizeof(host_tab));
+    MGP_REQUIRE(e == cudaSuccess, MGP_ERR_CUDA, "exp table upload: %s", cudaGetErrorString(e));
+    table_ready = true;
+  }
+  TileArgs a;
+  a.train_x = p->train_x;
+  a.query_x = p->query_x;
+  a.query_idx = p->query_idx;
+  a.nn_idx = p->nn_idx;
+  a.train_y = p->train_y;
+  a.noise_bk = p->noise_bk;
+  a.mean = p->mean;
+  a.var = p->var;
+  a.yky = p->yky;
+  a.coeffs = p->coeffs;
+  a.status = p->status;
+  a.b = p->b;
+  a.k = p->k;
+  a.kp = (p->k + 3) & ~3;
+  a.d = p->d;
+  a.r = p->r;
+  a.n_elem = p->k * (p->k + 1) / 2 + p->k;
+  a.noise = p->noise;
+  a.scale = p->scale;
+  a.kernel_id = model.kernel_id;
+  a.metric_id = model.metric_id;
+  // fold length scale (and the Matern sqrt(2 nu) factor for l2) into the coordinates
+  double kconst = 1.0;
+  if (model.kernel_id == MGP_KERNEL_MATERN_15) kconst = 1.7320508075688772;
+  if (model.kernel_id == MGP_KERNEL_MATERN_25) kconst = 2.23606797749979;
+  a.post_scale = 1.0;
+  for (int f = 0; f < TILE_MAX_D; ++f) a.coord_scale[f] = 1.0;
+  for (int f = 0; f < p->d; ++f) {
+    double inv = model.aniso ? model.inv_ls_vec[f]
+                             : (model.metric_id == MGP_METRIC_L2 ? model.inv_ls
+                                                                  : sqrt(model.inv_ls));
+    a.coord_scale[f] = (model.metric_id == MGP_METRIC_L2) ? inv * kconst : inv;
+  }
+  if (model.metric_id == MGP_METRIC_F2) a.post_scale = kconst;
+
+  const int T = tiles_needed(p->k, p->r);
+  const int NT = T * (T + 1) / 2;
+  size_t warp_doubles = (size_t)NT * 64 + (size_t)(p->k + 1) * p->d;
+  warp_doubles = (warp_doubles + 1) & ~(size_t)1;  // keep 16-byte alignment of tiles
+  const size_t shared_doubles = EXP_TABLE + (size_t)((((a.n_elem + 3) / 4) + 1) & ~1);
+  const size_t smem = (shared_doubles + warp_doubles * TILE_WARPS) * sizeof(double);
+  MGP_REQUIRE(smem <= (size_t)max_smem_optin(), MGP_ERR_UNSUPPORTED,
+              "tile kernel shared memory %zu too large", smem);
+  long long blocks = (p->b + TILE_WARPS - 1) / TILE_WARPS;
+  const long long cap = (long long)sm_count() * 3;
+  if (blocks > cap) blocks = cap;
+#define MGP_TILE(TT)                                                                          \
+  case TT:                                                                                    \
+    cudaFuncSetAttribute(fused_tile_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                         (int)smem);                                                          \
+    fused_tile_kernel<TT><<<(unsigned)blocks, TILE_WARPS * 32, smem, stream>>>(a, warp_doubles); \
+    break;
+  switch (T) {
+    MGP_TILE(1)
+    MGP_TILE(2)
+    MGP_TILE(3)
+    MGP_TILE(4)
+    MGP_TILE(5)
+    MGP_TILE(6)
+    MGP_TILE(7)
+    default:
+      set_error("tile variant does not support %d tile rows", T);
+      return MGP_ERR_UNSUPPORTED;
+  }
+#undef MGP_TILE
+  return check_launch("fused_tile_kernel");
 }
 
 }  // namespace mgp
+
+extern "C" int mgp_set_fused_variant(int32_t variant) {
+  if (variant < 0 || variant > 2) {
+    mgp::set_error("variant must be 0 (auto), 1 (generic) or 2 (tile)");
+    return MGP_ERR_BAD_ARG;
+  }
+  mgp::g_variant = variant;
+  return MGP_OK;
+}

@@ -72,6 +72,11 @@ def as_2d(x: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # fused path
 # --------------------------------------------------------------------------
+def set_fused_variant(variant: int) -> None:
+    """0 = auto, 1 = generic shared-memory kernel, 2 = register-tile DMMA kernel."""
+    L.check(L.lib().mgp_set_fused_variant(int(variant)))
+
+
 def fused_posterior(
     train_x: torch.Tensor,
     query_x: torch.Tensor,

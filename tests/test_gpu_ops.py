@@ -30,11 +30,16 @@ def _2d(x):
     return x[:, None] if x.ndim == 1 else x
 
 
-@pytest.fixture(scope="module")
-def ops():
+@pytest.fixture(scope="module", params=["auto", "generic"])
+def ops(request):
+    """Every test runs twice: through the automatically chosen fused kernel (the
+    register-tile DMMA variant where the shape allows) and through the generic
+    shared-memory variant, two independently written implementations."""
     from muygpys_b200 import ops as _ops
 
-    return _ops
+    _ops.set_fused_variant(0 if request.param == "auto" else 1)
+    yield _ops
+    _ops.set_fused_variant(0)
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
