@@ -109,47 +109,133 @@ struct TileArgs {
   int k, kp, d, r;
   int n_elem;      // k(k+1)/2 + k table entries
   double noise, scale;
-  int kernel_id, metric_id;
+  int formula;     // Formula below
   double coord_scale[TILE_MAX_D];  // per-feature multiplier folded into staged coordinates
   double post_scale;               // F2 metric with Matern: s = post_scale * u2
+  int kernel_id;
 };
 
-// covariance from u2 = sum of squared prescaled differences
-__device__ __forceinline__ double cov_from_u2(const TileArgs& a, double u2, const double* tab64) {
-  if (a.metric_id == MGP_METRIC_L2) {
-    switch (a.kernel_id) {
-      case MGP_KERNEL_MATERN_05:
-        return exp_neg(sqrt_fast(u2), tab64);
-      case MGP_KERNEL_MATERN_15: {
-        const double s = sqrt_fast(u2);
-        return (1.0 + s) * exp_neg(s, tab64);
-      }
-      case MGP_KERNEL_MATERN_25: {
-        const double s = sqrt_fast(u2);
-        return fma(u2, 1.0 / 3.0, 1.0 + s) * exp_neg(s, tab64);
-      }
-      case MGP_KERNEL_MATERN_INF:
-        return exp_neg(0.5 * u2, tab64);
-      default:  // RBF fed with l2 distances: exp(-x/2)
-        return exp_neg(0.5 * sqrt_fast(u2), tab64);
-    }
+// covariance as a function of u2 = sum of squared prescaled coordinate differences
+enum Formula {
+  F_M05 = 0,     // exp(-sqrt(u2))
+  F_M15 = 1,     // (1+s) exp(-s),          s = sqrt(u2)   (sqrt(3)/l folded into coordinates)
+  F_M25 = 2,     // (1+s+u2/3) exp(-s),     s = sqrt(u2)   (sqrt(5)/l folded)
+  F_GAUSS = 3,   // exp(-u2/2): RBF on F2, Matern nu=inf on l2
+  F_RBF_L2 = 4,  // exp(-sqrt(u2)/2): RBF handed l2 distances (reference quirk, rbf.py:74-76)
+  F_F2_ANY = 5   // any other kernel fed the squared metric: argument post_scale*u2
+};
+
+template <int F>
+__device__ __forceinline__ double cov_from_u2(double u2, const double* tab64, double post_scale,
+                                              int kernel_id) {
+  if (F == F_M05) return exp_neg(sqrt_fast(u2), tab64);
+  if (F == F_M15) {
+    const double s = sqrt_fast(u2);
+    return (1.0 + s) * exp_neg(s, tab64);
   }
-  const double s = a.post_scale * u2;  // F2: the kernel argument is the squared form
-  switch (a.kernel_id) {
-    case MGP_KERNEL_RBF:
-      return exp_neg(0.5 * s, tab64);
+  if (F == F_M25) {
+    const double s = sqrt_fast(u2);
+    return fma(u2, 1.0 / 3.0, 1.0 + s) * exp_neg(s, tab64);
+  }
+  if (F == F_GAUSS) return exp_neg(0.5 * u2, tab64);
+  if (F == F_RBF_L2) return exp_neg(0.5 * sqrt_fast(u2), tab64);
+  const double s = post_scale * u2;
+  switch (kernel_id) {
     case MGP_KERNEL_MATERN_05:
       return exp_neg(s, tab64);
     case MGP_KERNEL_MATERN_15:
       return (1.0 + s) * exp_neg(s, tab64);
     case MGP_KERNEL_MATERN_25:
       return fma(s * s, 1.0 / 3.0, 1.0 + s) * exp_neg(s, tab64);
-    default:
+    default:  // Matern inf on the squared metric
       return exp_neg(0.5 * s * s, tab64);
   }
 }
 
-__device__ __forceinline__ int tile_base(int I, int J) { return ((I * (I + 1)) / 2 + J) * 64; }
+template <int D>
+__device__ __forceinline__ double sqdist(const double* __restrict__ pts, int pi, int j, int d) {
+  if (D == 1) {
+    const double df = pts[pi] - pts[j];
+    return df * df;
+  }
+  if (D == 2) {
+    const double2 p = reinterpret_cast<const double2*>(pts)[pi];
+    const double2 c = reinterpret_cast<const double2*>(pts)[j];
+    const double dx = p.x - c.x, dy = p.y - c.y;
+    return fma(dy, dy, dx * dx);
+  }
+  if (D == 3) {
+    const double dx = pts[3 * pi] - pts[3 * j], dy = pts[3 * pi + 1] - pts[3 * j + 1],
+                 dz = pts[3 * pi + 2] - pts[3 * j + 2];
+    return fma(dz, dz, fma(dy, dy, dx * dx));
+  }
+  double u2 = 0.0;
+  for (int f = 0; f < d; ++f) {
+    const double df = pts[pi * d + f] - pts[j * d + f];
+    u2 = fma(df, df, u2);
+  }
+  return u2;
+}
+
+// Flat, perfectly balanced evaluation of the k(k+1)/2 + k covariances; each table
+// entry is (tile-image offset << 16) | (row point << 8) | column point.  Writes
+// N = -K.  Compiled once per (formula, D) and called from every tile kernel.
+template <int F, int D>
+__device__ __noinline__ void assemble(double* __restrict__ tiles, const double* __restrict__ pts,
+                                      const unsigned* __restrict__ etab,
+                                      const double* __restrict__ tab64, int n_elem, int lane,
+                                      int d, double post_scale, int kernel_id) {
+  int e = lane;
+  for (; e + 32 < n_elem; e += 64) {  // two independent elements in flight
+    const unsigned p0 = etab[e], p1 = etab[e + 32];
+    const double u0 = sqdist<D>(pts, (p0 >> 8) & 255, p0 & 255, d);
+    const double u1 = sqdist<D>(pts, (p1 >> 8) & 255, p1 & 255, d);
+    const double v0 = cov_from_u2<F>(u0, tab64, post_scale, kernel_id);
+    const double v1 = cov_from_u2<F>(u1, tab64, post_scale, kernel_id);
+    tiles[p0 >> 16] = -v0;
+    tiles[p1 >> 16] = -v1;
+  }
+  if (e < n_elem) {
+    const unsigned p0 = etab[e];
+    const double u0 = sqdist<D>(pts, (p0 >> 8) & 255, p0 & 255, d);
+    tiles[p0 >> 16] = -cov_from_u2<F>(u0, tab64, post_scale, kernel_id);
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void assemble_d(double* tiles, const double* pts, const unsigned* etab,
+                                           const double* tab64, int n_elem, int lane, int d,
+                                           double post_scale, int kernel_id) {
+  switch (d) {
+    case 1: assemble<F, 1>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    case 2: assemble<F, 2>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    case 3: assemble<F, 3>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    default: assemble<F, 0>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id);
+  }
+}
+
+__device__ __forceinline__ void assemble_any(int formula, double* tiles, const double* pts,
+                                             const unsigned* etab, const double* tab64,
+                                             int n_elem, int lane, int d, double post_scale,
+                                             int kernel_id) {
+  switch (formula) {
+    case F_M05: assemble_d<F_M05>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    case F_M15: assemble_d<F_M15>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    case F_M25: assemble_d<F_M25>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    case F_GAUSS: assemble_d<F_GAUSS>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    case F_RBF_L2: assemble_d<F_RBF_L2>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    default: assemble_d<F_F2_ANY>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id);
+  }
+}
+
+__host__ __device__ __forceinline__ int tile_base(int I, int J) {
+  return ((I * (I + 1)) / 2 + J) * 64;
+}
+__device__ __forceinline__ int elem_off(int i, int j) {
+  return tile_base(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7);
+}
+
+__device__ __forceinline__ double sel_d(bool p, double a, double b) { return p ? a : b; }
 
 template <int T>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
@@ -160,40 +246,50 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
   const int rho = lane >> 2, q = lane & 3;
   const int k = a.k, kp = a.kp, d = a.d, r = a.r;
 
-  // CTA-shared: exp table and the (tile row, column) table of the flat element list
+  // CTA-shared: exp table and the table of the flat element list
   double* tab64 = smem;
-  unsigned short* etab = (unsigned short*)(tab64 + EXP_TABLE);
-  const int etab_doubles = (((a.n_elem + 3) / 4) + 1) & ~1;
+  unsigned* etab = (unsigned*)(tab64 + EXP_TABLE);
+  const int etab_doubles = (((a.n_elem + 1) / 2) + 1) & ~1;
   double* wbase = tab64 + EXP_TABLE + etab_doubles + (size_t)warp * warp_doubles;
-  double* tiles = wbase;               // NT * 64 doubles, tile-major, row-major inside
-  double* pts = tiles + NT * 64;       // (k+1) x d prescaled coordinates, row k = query
+  double* tiles = wbase;          // NT * 64 doubles, tile-major, row-major inside a tile
+  double* pts = tiles + NT * 64;  // (k+1) x d prescaled coordinates, row k = query
 
   for (int j = threadIdx.x; j < EXP_TABLE; j += blockDim.x) tab64[j] = c_exp_tab[j];
   for (int e = threadIdx.x; e < a.n_elem; e += blockDim.x) {
     // e < k(k+1)/2: lower triangle in row-major order; then the k cross entries
     const int tri = k * (k + 1) / 2;
-    int ti, j;
+    int ti, pi, j;
     if (e < tri) {
       int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
       while ((i + 1) * (i + 2) / 2 <= e) ++i;
       while (i * (i + 1) / 2 > e) --i;
-      ti = i;
+      ti = pi = i;
       j = e - i * (i + 1) / 2;
     } else {
       ti = kp;
+      pi = k;
       j = e - tri;
     }
-    etab[e] = (unsigned short)((ti << 8) | j);
+    etab[e] = ((unsigned)elem_off(ti, j) << 16) | ((unsigned)pi << 8) | (unsigned)j;
   }
   __syncthreads();
 
   const long long wglobal = (long long)blockIdx.x * TILE_WARPS + warp;
   const long long wstride = (long long)gridDim.x * TILE_WARPS;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  // per-lane constants of the accumulator -> fragment re-layout (see below)
+  const int qb = lane & ~3;
+  const int srcA = qb | ((0x3102 >> (4 * q)) & 3);
+  const int srcB = qb | ((0x1320 >> (4 * q)) & 3);
+  const int zero_from = (k >> 3);  // first tile row that holds padding / augmented rows
 
   for (long long row = wglobal; row < a.b; row += wstride) {
-    // ---- zero the tile image, stage coordinates and targets ----------------
-    for (int e = lane; e < NT * 32; e += 32) reinterpret_cast<double2*>(tiles)[e] = make_double2(0.0, 0.0);
+    // ---- zero the tile rows that keep padding, stage coordinates and targets ----
+    {
+      double2* z = reinterpret_cast<double2*>(tiles + tile_base(zero_from, 0));
+      const int cnt = (NT * 64 - tile_base(zero_from, 0)) / 2;
+      for (int e = lane; e < cnt; e += 32) z[e] = make_double2(0.0, 0.0);
+    }
     __syncwarp();
     const long long qrow = a.query_idx ? a.query_idx[row] : row;
     for (int i = lane; i <= k; i += 32) {
@@ -202,36 +298,23 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
       const double* px = (is_q ? a.query_x : a.train_x) + src * d;
       for (int f = 0; f < d; ++f) pts[i * d + f] = px[f] * a.coord_scale[f];
       if (!is_q && a.train_y) {
-        for (int c = 0; c < r; ++c) {  // augmented rows kp+1+c hold -y (tiles hold N = -A)
-          const int ti = kp + 1 + c;
-          tiles[tile_base(ti >> 3, i >> 3) + (ti & 7) * 8 + (i & 7)] = -a.train_y[src * r + c];
-        }
+        for (int c = 0; c < r; ++c)  // augmented rows kp+1+c hold -y (tiles hold N = -A)
+          tiles[elem_off(kp + 1 + c, i)] = -a.train_y[src * r + c];
       }
     }
     // identity padding rows k..kp-1 and Kout = 1 at (kp,kp)
-    if (lane <= kp - k) {
-      const int i = k + lane;
-      tiles[tile_base(i >> 3, i >> 3) + (i & 7) * 9] = -1.0;
-    }
+    if (lane <= kp - k) tiles[elem_off(k + lane, k + lane)] = -1.0;
     __syncwarp();
 
-    // ---- covariance assembly: flat balanced loop ---------------------------
-    for (int e = lane; e < a.n_elem; e += 32) {
-      const int packed = etab[e];
-      const int ti = packed >> 8, j = packed & 255;
-      const int pi = (ti == kp) ? k : ti;
-      double u2 = 0.0;
-      for (int f = 0; f < d; ++f) {
-        const double df = pts[pi * d + f] - pts[j * d + f];
-        u2 = fma(df, df, u2);
-      }
-      double v = cov_from_u2(a, u2, tab64);
-      if (ti == j) v += a.noise_bk ? a.noise_bk[row * k + j] : a.noise;
-      tiles[tile_base(ti >> 3, j >> 3) + (ti & 7) * 8 + (j & 7)] = -v;
-    }
+    // ---- covariance assembly -------------------------------------------------
+    assemble_any(a.formula, tiles, pts, etab, tab64, a.n_elem, lane, d, a.post_scale,
+                 a.kernel_id);
+    __syncwarp();
+    for (int i = lane; i < k; i += 32)  // nugget on the diagonal (N = -(K + eps))
+      tiles[elem_off(i, i)] -= a.noise_bk ? a.noise_bk[row * k + i] : a.noise;
     __syncwarp();
 
-    // ---- left-looking tiled Cholesky in registers ---------------------------
+    // ---- left-looking tiled Cholesky in registers -----------------------------
     double la_lo[T][T], la_hi[T][T];  // [I][P], I > P: finished tiles as A/B fragments
     bool ok = true;
 #pragma unroll
@@ -239,7 +322,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
       double c[T][2];
 #pragma unroll
       for (int I = J; I < T; ++I) {
-        const double2 v = *reinterpret_cast<const double2*>(tiles + tile_base(I, J) + rho * 8 + 2 * q);
+        const double2 v =
+            *reinterpret_cast<const double2*>(tiles + tile_base(I, J) + rho * 8 + 2 * q);
         c[I][0] = v.x;
         c[I][1] = v.y;
       }
@@ -270,53 +354,32 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
             const double p = shfl_d(c[J][bj], j * 4 + qj);
             ok = ok && (p > 0.0);
             const double rinv = rsqrt_fast(p);
+            const double fac = sel_d(q == qj, rinv, 1.0);  // only column j is scaled
 #pragma unroll
-            for (int I = J; I < T; ++I)
-              if (q == qj) c[I][bj] *= rinv;
-            double lc0 = shfl_d(c[J][bj], (2 * q) * 4 + qj);
-            double lc1 = shfl_d(c[J][bj], (2 * q + 1) * 4 + qj);
-            lc0 = (2 * q > j) ? lc0 : 0.0;
-            lc1 = (2 * q + 1 > j) ? lc1 : 0.0;
+            for (int I = J; I < T; ++I) c[I][bj] *= fac;
+            // L[c][j] for this lane's two columns c = 2q, 2q+1 (zero for finished columns)
+            const double lc0 = sel_d(2 * q > j, shfl_d(c[J][bj], (2 * q) * 4 + qj), 0.0);
+            const double lc1 = sel_d(2 * q + 1 > j, shfl_d(c[J][bj], (2 * q + 1) * 4 + qj), 0.0);
+            const int src_row = qb | qj;
 #pragma unroll
             for (int I = J; I < T; ++I) {
-              const double lr = shfl_d(c[I][bj], (lane & ~3) | qj);
+              const double lr = shfl_d(c[I][bj], src_row);  // L[row][j]
               if (j < 6) c[I][0] = fma(-lr, lc0, c[I][0]);
               if (j < 7) c[I][1] = fma(-lr, lc1, c[I][1]);
             }
           }
         }
-        // re-layout the finished tiles below the diagonal into A/B fragments
+        // re-layout the finished tiles below the diagonal into A/B fragments:
+        // quad permutation {0,1},{2,3},{4,5},{6,7} -> {0,4},{1,5},{2,6},{3,7} in 2 rounds
         if (J + 1 < T) {
-          const int kap = q;  // fragment column this lane owns
 #pragma unroll
           for (int I = J + 1; I < T; ++I) {
-            // quad permutation {0,1},{2,3},{4,5},{6,7} -> {0,4},{1,5},{2,6},{3,7} in 2 rounds
-            const int qb = lane & ~3;
-            // round A: lanes present L0:c1 L1:c0 L2:c0 L3:c0 ; readers L1<-L0 L2<-L1 L0<-L2
-            const double presA = (q == 0) ? c[I][1] : c[I][0];
-            const int srcA = qb | ((q == 1) ? 0 : (q == 2) ? 1 : (q == 0) ? 2 : 3);
-            const double gotA = shfl_d(presA, srcA);
-            // round B: L1:c1 L2:c1 L3:c0 ; readers L3<-L1 L1<-L2 L2<-L3
-            const double presB = (q == 3) ? c[I][0] : c[I][1];
-            const int srcB = qb | ((q == 3) ? 1 : (q == 1) ? 2 : (q == 2) ? 3 : 0);
-            const double gotB = shfl_d(presB, srcB);
-            // lane kap needs cols kap (lo) and 4+kap (hi)
-            double lo, hi;
-            if (kap == 0) {
-              lo = c[I][0];  // col 0 (own)
-              hi = gotA;     // col 4 from L2
-            } else if (kap == 1) {
-              lo = gotA;     // col 1 from L0
-              hi = gotB;     // col 5 from L2
-            } else if (kap == 2) {
-              lo = gotA;     // col 2 from L1
-              hi = gotB;     // col 6 from L3
-            } else {
-              lo = gotB;     // col 3 from L1
-              hi = c[I][1];  // col 7 (own)
-            }
-            la_lo[I][J] = lo;
-            la_hi[I][J] = hi;
+            // round A presents L0:c1 L1:c0 L2:c0 L3:c0 ; readers L1<-L0 L2<-L1 L0<-L2
+            const double gotA = shfl_d(sel_d(q == 0, c[I][1], c[I][0]), srcA);
+            // round B presents L1:c1 L2:c1 L3:c0 ; readers L3<-L1 L1<-L2 L2<-L3
+            const double gotB = shfl_d(sel_d(q == 3, c[I][0], c[I][1]), srcB);
+            la_lo[I][J] = sel_d(q == 0, c[I][0], sel_d(q == 3, gotB, gotA));
+            la_hi[I][J] = sel_d(q == 0, gotA, sel_d(q == 3, c[I][1], gotB));
           }
         }
       }
@@ -330,42 +393,37 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
     }
     __syncwarp();
 
-    // ---- outputs from the Schur complement ----------------------------------
-    auto elem = [&](int i, int j) -> double {
-      return tiles[tile_base(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7)];
-    };
+    // ---- outputs from the Schur complement -------------------------------------
     if (lane == 0) {
-      if (a.var) a.var[row] = ok ? a.scale * elem(kp, kp) : nan;
+      if (a.var) a.var[row] = ok ? a.scale * tiles[elem_off(kp, kp)] : nan;
       if (a.status) a.status[row] = ok ? 0 : 1;
       if (a.yky) {
         double s = 0.0;
-        for (int c2 = 0; c2 < r; ++c2) s -= elem(kp + 1 + c2, kp + 1 + c2);
+        for (int c2 = 0; c2 < r; ++c2) s -= tiles[elem_off(kp + 1 + c2, kp + 1 + c2)];
         a.yky[row] = ok ? s : nan;
       }
     }
     if (a.mean)
-      for (int c2 = lane; c2 < r; c2 += 32) a.mean[row * r + c2] = ok ? -elem(kp + 1 + c2, kp) : nan;
+      for (int c2 = lane; c2 < r; c2 += 32)
+        a.mean[row * r + c2] = ok ? -tiles[elem_off(kp + 1 + c2, kp)] : nan;
     if (a.coeffs) {
       // back substitution L^T C = U on the tile image (rows kp+1+c hold U^T)
       for (int i = k - 1; i >= 0; --i) {
-        const double inv = 1.0 / elem(i, i);
+        const double inv = 1.0 / tiles[elem_off(i, i)];
         __syncwarp();
-        for (int c2 = lane; c2 < r; c2 += 32) {
-          const int ti = kp + 1 + c2;
-          tiles[tile_base(ti >> 3, i >> 3) + (ti & 7) * 8 + (i & 7)] *= inv;
-        }
+        for (int c2 = lane; c2 < r; c2 += 32) tiles[elem_off(kp + 1 + c2, i)] *= inv;
         __syncwarp();
         for (int e = lane; e < r * i; e += 32) {
           const int c2 = e / i, j = e - c2 * i;
           const int ti = kp + 1 + c2;
-          double* dst = &tiles[tile_base(ti >> 3, j >> 3) + (ti & 7) * 8 + (j & 7)];
-          *dst = fma(-elem(ti, i), elem(i, j), *dst);
+          double* dst = &tiles[elem_off(ti, j)];
+          *dst = fma(-tiles[elem_off(ti, i)], tiles[elem_off(i, j)], *dst);
         }
         __syncwarp();
       }
       for (int e = lane; e < k * r; e += 32) {
         const int j = e / r, c2 = e - j * r;
-        a.coeffs[(row * k + j) * r + c2] = ok ? elem(kp + 1 + c2, j) : nan;
+        a.coeffs[(row * k + j) * r + c2] = ok ? tiles[elem_off(kp + 1 + c2, j)] : nan;
       }
     }
     __syncwarp();
@@ -422,7 +480,17 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
   a.noise = p->noise;
   a.scale = p->scale;
   a.kernel_id = model.kernel_id;
-  a.metric_id = model.metric_id;
+  if (model.metric_id == MGP_METRIC_L2) {
+    switch (model.kernel_id) {
+      case MGP_KERNEL_MATERN_05: a.formula = F_M05; break;
+      case MGP_KERNEL_MATERN_15: a.formula = F_M15; break;
+      case MGP_KERNEL_MATERN_25: a.formula = F_M25; break;
+      case MGP_KERNEL_MATERN_INF: a.formula = F_GAUSS; break;
+      default: a.formula = F_RBF_L2;
+    }
+  } else {
+    a.formula = (model.kernel_id == MGP_KERNEL_RBF) ? F_GAUSS : F_F2_ANY;
+  }
   // fold length scale (and the Matern sqrt(2 nu) factor for l2) into the coordinates
   double kconst = 1.0;
   if (model.kernel_id == MGP_KERNEL_MATERN_15) kconst = 1.7320508075688772;
@@ -441,7 +509,7 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
   const int NT = T * (T + 1) / 2;
   size_t warp_doubles = (size_t)NT * 64 + (size_t)(p->k + 1) * p->d;
   warp_doubles = (warp_doubles + 1) & ~(size_t)1;  // keep 16-byte alignment of tiles
-  const size_t shared_doubles = EXP_TABLE + (size_t)((((a.n_elem + 3) / 4) + 1) & ~1);
+  const size_t shared_doubles = EXP_TABLE + (size_t)((((a.n_elem + 1) / 2) + 1) & ~1);
   const size_t smem = (shared_doubles + warp_doubles * TILE_WARPS) * sizeof(double);
   MGP_REQUIRE(smem <= (size_t)max_smem_optin(), MGP_ERR_UNSUPPORTED,
               "tile kernel shared memory %zu too large", smem);
