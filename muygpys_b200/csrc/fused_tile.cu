@@ -237,6 +237,27 @@ __device__ __forceinline__ int elem_off(int i, int j) {
 
 __device__ __forceinline__ double sel_d(bool p, double a, double b) { return p ? a : b; }
 
+// 1/p: MUFU.RCP64H seed (~20 bits) + one third-order step (error ~ 2^-60), depth 3
+__device__ __forceinline__ double rcp_fast(double p) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+  const double e = fma(-p, r, 1.0);
+  const double q1 = r * e;
+  const double w = 1.0 + e;
+  return fma(q1, w, r);
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 template <int T>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
     fused_tile_kernel(const TileArgs a, size_t warp_doubles) {
@@ -251,8 +272,11 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
   unsigned* etab = (unsigned*)(tab64 + EXP_TABLE);
   const int etab_doubles = (((a.n_elem + 1) / 2) + 1) & ~1;
   double* wbase = tab64 + EXP_TABLE + etab_doubles + (size_t)warp * warp_doubles;
-  double* tiles = wbase;          // NT * 64 doubles, tile-major, row-major inside a tile
-  double* pts = tiles + NT * 64;  // (k+1) x d prescaled coordinates, row k = query
+  double* tiles = wbase;  // NT * 64 doubles, tile-major, row-major inside a tile
+  const int pts_doubles = ((k + 1) * d + 1) & ~1;
+  const int ys_doubles = (k * r + 1) & ~1;
+  double* pts_buf = tiles + NT * 64;           // 2 x (k+1) x d coordinates, row k = query
+  double* ys_buf = pts_buf + 2 * pts_doubles;  // 2 x k x r targets
 
   for (int j = threadIdx.x; j < EXP_TABLE; j += blockDim.x) tab64[j] = c_exp_tab[j];
   for (int e = threadIdx.x; e < a.n_elem; e += blockDim.x) {
@@ -277,31 +301,59 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
   const long long wglobal = (long long)blockIdx.x * TILE_WARPS + warp;
   const long long wstride = (long long)gridDim.x * TILE_WARPS;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  // per-lane constants of the accumulator -> fragment re-layout (see below)
   const int qb = lane & ~3;
-  const int srcA = qb | ((0x3102 >> (4 * q)) & 3);
-  const int srcB = qb | ((0x1320 >> (4 * q)) & 3);
   const int zero_from = (k >> 3);  // first tile row that holds padding / augmented rows
 
-  for (long long row = wglobal; row < a.b; row += wstride) {
-    // ---- zero the tile rows that keep padding, stage coordinates and targets ----
+  // ---- software pipeline over neighbourhoods: indices 2 ahead, rows 1 ahead (cp.async) ----
+  // lane l stages points l and l+32 (point k is the query)
+  auto load_src = [&](long long row, int i) -> long long {
+    if (row >= a.b || i > k) return -1;
+    if (i == k) return a.query_idx ? a.query_idx[row] : row;
+    return a.nn_idx[row * k + i];
+  };
+  auto issue_rows = [&](int buf, int i, long long src) {
+    if (src < 0) return;
+    const double* px = ((i == k) ? a.query_x : a.train_x) + src * d;
+    double* dst = pts_buf + buf * pts_doubles + i * d;
+    for (int f = 0; f < d; ++f) cp_async8(dst + f, px + f);
+    if (i < k && a.train_y) {
+      const double* py = a.train_y + src * r;
+      double* dy = ys_buf + buf * ys_doubles + i * r;
+      for (int c = 0; c < r; ++c) cp_async8(dy + c, py + c);
+    }
+  };
+  long long src0 = load_src(wglobal, lane), src1 = load_src(wglobal, lane + 32);
+  issue_rows(0, lane, src0);
+  issue_rows(0, lane + 32, src1);
+  cp_async_commit();
+  src0 = load_src(wglobal + wstride, lane);
+  src1 = load_src(wglobal + wstride, lane + 32);
+  int buf = 0;
+
+  for (long long row = wglobal; row < a.b; row += wstride, buf ^= 1) {
+    // ---- zero the tile rows that keep padding (previous outputs were read already) ----
     {
       double2* z = reinterpret_cast<double2*>(tiles + tile_base(zero_from, 0));
       const int cnt = (NT * 64 - tile_base(zero_from, 0)) / 2;
       for (int e = lane; e < cnt; e += 32) z[e] = make_double2(0.0, 0.0);
     }
+    cp_async_wait_all();
     __syncwarp();
-    const long long qrow = a.query_idx ? a.query_idx[row] : row;
-    for (int i = lane; i <= k; i += 32) {
-      const bool is_q = (i == k);
-      const long long src = is_q ? qrow : a.nn_idx[row * k + i];
-      const double* px = (is_q ? a.query_x : a.train_x) + src * d;
-      for (int f = 0; f < d; ++f) pts[i * d + f] = px[f] * a.coord_scale[f];
-      if (!is_q && a.train_y) {
-        for (int c = 0; c < r; ++c)  // augmented rows kp+1+c hold -y (tiles hold N = -A)
-          tiles[elem_off(kp + 1 + c, i)] = -a.train_y[src * r + c];
+    // rows of the next neighbourhood start flowing in; its successor's indices follow
+    issue_rows(buf ^ 1, lane, src0);
+    issue_rows(buf ^ 1, lane + 32, src1);
+    cp_async_commit();
+    src0 = load_src(row + 2 * wstride, lane);
+    src1 = load_src(row + 2 * wstride, lane + 32);
+    double* pts = pts_buf + buf * pts_doubles;
+    const double* ys = ys_buf + buf * ys_doubles;
+    // fold the length scale(s) into the staged coordinates; scatter -y into rows kp+1+c
+    for (int e = lane; e < (k + 1) * d; e += 32) pts[e] *= a.coord_scale[e % d];
+    if (a.train_y)
+      for (int e = lane; e < k * r; e += 32) {
+        const int i = e / r, c = e - i * r;
+        tiles[elem_off(kp + 1 + c, i)] = -ys[e];
       }
-    }
     // identity padding rows k..kp-1 and Kout = 1 at (kp,kp)
     if (lane <= kp - k) tiles[elem_off(k + lane, k + lane)] = -1.0;
     __syncwarp();
@@ -314,8 +366,14 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
       tiles[elem_off(i, i)] -= a.noise_bk ? a.noise_bk[row * k + i] : a.noise;
     __syncwarp();
 
-    // ---- left-looking tiled Cholesky in registers -----------------------------
-    double la_lo[T][T], la_hi[T][T];  // [I][P], I > P: finished tiles as A/B fragments
+    // ---- left-looking tiled LDL^T in registers ---------------------------------
+    // Finished tiles hold U = L D (unscaled columns) in ACCUMULATOR layout (lane
+    // (rho,q): columns 2q, 2q+1).  Register 0 of every lane read as an A (or B)
+    // fragment is the 8x4 slice of the EVEN columns {0,2,4,6}, register 1 the slice
+    // of the odd columns; the contraction index of U_I D^-1 U_J^T may be visited in
+    // any order, so two DMMAs (even, odd) update a tile with no re-layout at all.
+    double l0[T][T], l1[T][T];  // [I][P], I > P
+    double dinv0[T], dinv1[T];  // 1/d for this lane's two columns of tile column P
     bool ok = true;
 #pragma unroll
     for (int J = 0; J < T; ++J) {
@@ -330,13 +388,11 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
 #pragma unroll
       for (int P = 0; P < J; ++P) {
         if (8 * P < kp) {  // tile column P carries eliminated columns
-          // half-eliminated tile column (kp % 8 == 4): only its first 4 columns are L
-          const bool full = (8 * P + 8 <= kp);
+          const double b0 = l0[J][P] * dinv0[P], b1 = l1[J][P] * dinv1[P];
 #pragma unroll
           for (int I = J; I < T; ++I) {
-            // the B fragment of tile (J,P) equals its A fragment (see header comment)
-            dmma_acc(c[I][0], c[I][1], la_lo[I][P], la_lo[J][P]);
-            if (full) dmma_acc(c[I][0], c[I][1], la_hi[I][P], la_hi[J][P]);
+            dmma_acc(c[I][0], c[I][1], l0[I][P], b0);
+            dmma_acc(c[I][0], c[I][1], l1[I][P], b1);
           }
         }
       }
@@ -347,39 +403,56 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
       }
       const int ncols = min(8, kp - 8 * J);  // eliminated columns in this tile column
       if (ncols > 0) {
+        // Column operations are right-multiplications by a matrix M that depends on the
+        // diagonal tile only.  Run them on the diagonal tile and on an identity tile V
+        // (-> V = M); every tile below the diagonal then becomes S*M with two DMMAs.
+        double v0 = (rho == 2 * q) ? 1.0 : 0.0, v1 = (rho == 2 * q + 1) ? 1.0 : 0.0;
+        double di0 = 0.0, di1 = 0.0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (j < ncols) {
             const int qj = j >> 1, bj = j & 1;
+            // everything below reads the (final, unscaled) column j at once
             const double p = shfl_d(c[J][bj], j * 4 + qj);
+            const double uc0 = shfl_d(c[J][bj], (2 * q) * 4 + qj);      // U[2q][j]
+            const double uc1 = shfl_d(c[J][bj], (2 * q + 1) * 4 + qj);  // U[2q+1][j]
+            const double lr = shfl_d(c[J][bj], qb | qj);                // U[row][j]
+            const double vr = shfl_d(bj == 0 ? v0 : v1, qb | qj);       // V[row][j]
             ok = ok && (p > 0.0);
-            const double rinv = rsqrt_fast(p);
-            const double fac = sel_d(q == qj, rinv, 1.0);  // only column j is scaled
-#pragma unroll
-            for (int I = J; I < T; ++I) c[I][bj] *= fac;
-            // L[c][j] for this lane's two columns c = 2q, 2q+1 (zero for finished columns)
-            const double lc0 = sel_d(2 * q > j, shfl_d(c[J][bj], (2 * q) * 4 + qj), 0.0);
-            const double lc1 = sel_d(2 * q + 1 > j, shfl_d(c[J][bj], (2 * q + 1) * 4 + qj), 0.0);
-            const int src_row = qb | qj;
-#pragma unroll
-            for (int I = J; I < T; ++I) {
-              const double lr = shfl_d(c[I][bj], src_row);  // L[row][j]
-              if (j < 6) c[I][0] = fma(-lr, lc0, c[I][0]);
-              if (j < 7) c[I][1] = fma(-lr, lc1, c[I][1]);
+            const double pinv = rcp_fast(p);
+            if (bj == 0) di0 = sel_d(q == qj, pinv, di0); else di1 = sel_d(q == qj, pinv, di1);
+            // U[c][j] / d_j for this lane's columns c = 2q, 2q+1 (zero for finished columns)
+            const double t0 = sel_d(2 * q > j, uc0, 0.0) * pinv;
+            const double t1 = sel_d(2 * q + 1 > j, uc1, 0.0) * pinv;
+            if (j < 6) {
+              c[J][0] = fma(-lr, t0, c[J][0]);
+              v0 = fma(-vr, t0, v0);
+            }
+            if (j < 7) {
+              c[J][1] = fma(-lr, t1, c[J][1]);
+              v1 = fma(-vr, t1, v1);
             }
           }
         }
-        // re-layout the finished tiles below the diagonal into A/B fragments:
-        // quad permutation {0,1},{2,3},{4,5},{6,7} -> {0,4},{1,5},{2,6},{3,7} in 2 rounds
+        // a half-eliminated tile column only contributes its first four columns later
+        const bool keep = (ncols == 8) || (q < 2);
+        dinv0[J] = sel_d(keep, di0, 0.0);
+        dinv1[J] = sel_d(keep, di1, 0.0);
         if (J + 1 < T) {
+          // B fragments of M: even rows {0,2,4,6} and odd rows, lane l = (kk = l&3, n = l>>2)
+          const int srcE = 8 * q + (lane >> 3), par = (lane >> 2) & 1;
+          const double e0 = shfl_d(v0, srcE), e1 = shfl_d(v1, srcE);
+          const double o0 = shfl_d(v0, srcE + 4), o1 = shfl_d(v1, srcE + 4);
+          const double bm0 = sel_d(par, e1, e0), bm1 = sel_d(par, o1, o0);
 #pragma unroll
           for (int I = J + 1; I < T; ++I) {
-            // round A presents L0:c1 L1:c0 L2:c0 L3:c0 ; readers L1<-L0 L2<-L1 L0<-L2
-            const double gotA = shfl_d(sel_d(q == 0, c[I][1], c[I][0]), srcA);
-            // round B presents L1:c1 L2:c1 L3:c0 ; readers L3<-L1 L1<-L2 L2<-L3
-            const double gotB = shfl_d(sel_d(q == 3, c[I][0], c[I][1]), srcB);
-            la_lo[I][J] = sel_d(q == 0, c[I][0], sel_d(q == 3, gotB, gotA));
-            la_hi[I][J] = sel_d(q == 0, gotA, sel_d(q == 3, c[I][1], gotB));
+            double n0 = 0.0, n1 = 0.0;
+            dmma_acc(n0, n1, c[I][0], bm0);
+            dmma_acc(n0, n1, c[I][1], bm1);
+            c[I][0] = n0;
+            c[I][1] = n1;
+            l0[I][J] = n0;
+            l1[I][J] = n1;
           }
         }
       }
@@ -393,7 +466,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
     }
     __syncwarp();
 
-    // ---- outputs from the Schur complement -------------------------------------
+    // ---- outputs from the Schur complement: lane 0 var/yky/status, lanes 1..r mean ----
     if (lane == 0) {
       if (a.var) a.var[row] = ok ? a.scale * tiles[elem_off(kp, kp)] : nan;
       if (a.status) a.status[row] = ok ? 0 : 1;
@@ -402,12 +475,14 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
         for (int c2 = 0; c2 < r; ++c2) s -= tiles[elem_off(kp + 1 + c2, kp + 1 + c2)];
         a.yky[row] = ok ? s : nan;
       }
-    }
-    if (a.mean)
-      for (int c2 = lane; c2 < r; c2 += 32)
+    } else if (a.mean) {
+      for (int c2 = lane - 1; c2 < r; c2 += 31)
         a.mean[row * r + c2] = ok ? -tiles[elem_off(kp + 1 + c2, kp)] : nan;
+    }
     if (a.coeffs) {
-      // back substitution L^T C = U on the tile image (rows kp+1+c hold U^T)
+      // The image holds U = L D (L unit lower) and, in rows kp+1+c, u = L^-1 y.  With
+      // K^-1 y = L^-T D^-1 u:  C_i = (u_i - sum_{j>i} U[j][i] C_j) / d_i, column by column.
+      __syncwarp();
       for (int i = k - 1; i >= 0; --i) {
         const double inv = 1.0 / tiles[elem_off(i, i)];
         __syncwarp();
@@ -428,6 +503,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
     }
     __syncwarp();
   }
+  cp_async_wait_all();
 }
 
 static int tiles_needed(int k, int r) {
@@ -507,8 +583,9 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
 
   const int T = tiles_needed(p->k, p->r);
   const int NT = T * (T + 1) / 2;
-  size_t warp_doubles = (size_t)NT * 64 + (size_t)(p->k + 1) * p->d;
-  warp_doubles = (warp_doubles + 1) & ~(size_t)1;  // keep 16-byte alignment of tiles
+  // per warp: tile image + double-buffered coordinates and targets (cp.async prefetch)
+  const size_t warp_doubles = (size_t)NT * 64 + 2 * (size_t)((((p->k + 1) * p->d) + 1) & ~1) +
+                              2 * (size_t)(((p->k * p->r) + 1) & ~1);
   const size_t shared_doubles = EXP_TABLE + (size_t)((((a.n_elem + 1) / 2) + 1) & ~1);
   const size_t smem = (shared_doubles + warp_doubles * TILE_WARPS) * sizeof(double);
   MGP_REQUIRE(smem <= (size_t)max_smem_optin(), MGP_ERR_UNSUPPORTED,
