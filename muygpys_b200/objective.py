@@ -21,8 +21,8 @@ from .distributed import allreduce_partials
 from .losses import LossFn
 
 
-def _finish_loss(loss_fn: LossFn, rec, k: int, scale_obj, model=None) -> float:
-    """Turn an (all-reduced) partials record into the reference's loss value."""
+def _finish_loss(loss_fn: LossFn, rec) -> float:
+    """Turn an (all-reduced) partials record of a variance-free loss into its value."""
     if loss_fn.loss_id == L.LOSS_MSE:
         return rec[L.P_SQERR] / rec[L.P_COUNT]
     return rec[L.P_AUX]
@@ -99,20 +99,20 @@ def make_fused_loo_crossval_fn(muygps, loss_fn: LossFn, batch_indices, batch_nn_
         if not needs_var:
             rec = ops.loss_partials(loss_fn.loss_id, mean, y_b, boundary_scale=delta)
             rec = reduce(rec).cpu().numpy()
-            return -float(_finish_loss(loss_fn, rec, k, muygps.scale))
+            return -float(_finish_loss(loss_fn, rec))
         var = out["var"]
         if analytic:
-            # pass 1: everything that is linear in the rows, incl. sum y^T K^-1 y
-            rec = ops.loss_partials(L.LOSS_NONE, mean, y_b, var=var, yky=yky)
             if loss_fn.loss_id == L.LOSS_LOOL:
-                # lool is affine in 1/sigma^2 and log sigma^2: one all-reduce is enough
-                ops.loss_partials(L.LOSS_LOOL, mean, y_b, var=var, partials=rec)
+                # lool is affine in 1/sigma^2 and log sigma^2, so the per-rank sums of
+                # e^2/v, log v and y^T K^-1 y finish it after ONE all-reduce
+                rec = ops.loss_partials(L.LOSS_LOOL, mean, y_b, var=var, yky=yky)
                 rec = reduce(rec).cpu().numpy()
-                rows = rec[L.P_ROWS] / 2.0  # both passes counted the rows
+                rows = rec[L.P_ROWS]
                 sigma2 = muygps.scale.from_mean_quadratic_form(rec[L.P_YKY] / (rows * k))
                 loss = rec[L.P_SQERR_V] / sigma2 + rec[L.P_LOGV] + rows * math.log(sigma2)
                 return -float(loss)
-            rec = reduce(rec)
+            # looph is nonlinear in sigma^2: reduce the scale first, then the loss
+            rec = reduce(ops.loss_partials(L.LOSS_NONE, mean, y_b, var=var, yky=yky))
             sigma0 = rec[L.P_YKY] / (rec[L.P_ROWS] * k)
             sigma2_dev = _iterate_scale(sigma0, muygps.scale.iteration_count).reshape(1)
         else:

@@ -1,0 +1,259 @@
+"""GPU parity at the reference's API level: the host mirror (MuyGPS, kernels,
+deformations, NN_Wrapper, losses, optimisers, *_from_indices) against the
+reference's recorded outputs.  Reads like tests/backend/torch_correctness.py of
+the reference: build the model objects, run the staged and the fused pipelines,
+compare within the north-star tolerance."""
+
+import copy
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_oracle as O
+from oracle.cases import CASES, by_name, make_data
+
+from conftest import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _mods():
+    from muygpys_b200.gp import MuyGPS
+    from muygpys_b200.gp.deformation import F2, Anisotropy, Isotropy, l2
+    from muygpys_b200.gp.hyperparameter import (AnalyticScale, FixedScale, Parameter,
+                                                VectorParameter)
+    from muygpys_b200.gp.kernels import RBF, Matern
+    from muygpys_b200.gp.noise import HeteroscedasticNoise, HomoscedasticNoise
+
+    return locals()
+
+
+SMOOTH = {O.KERNEL_MATERN_05: 0.5, O.KERNEL_MATERN_15: 1.5, O.KERNEL_MATERN_25: 2.5,
+          O.KERNEL_MATERN_INF: math.inf}
+
+
+def build_model(case, noise=None, opt_bounds=False, scale=None):
+    m = _mods()
+    metric = m["l2"] if case.metric_id == O.METRIC_L2 else m["F2"]
+    P = m["Parameter"]
+
+    def par(v):
+        return P(v, (v * 0.1, v * 10.0)) if opt_bounds else P(v)
+
+    if case.anisotropic:
+        deformation = m["Anisotropy"](metric, m["VectorParameter"](*[par(v) for v in
+                                                                      case.length_scale]))
+    else:
+        deformation = m["Isotropy"](metric, par(case.length_scale))
+    if case.kernel_id == O.KERNEL_RBF:
+        kernel = m["RBF"](deformation=deformation)
+    else:
+        kernel = m["Matern"](smoothness=P(SMOOTH[case.kernel_id]), deformation=deformation)
+    return m["MuyGPS"](kernel=kernel, noise=noise or m["HomoscedasticNoise"](case.noise),
+                       scale=scale or m["FixedScale"]())
+
+
+def theta_kwargs(case, factor):
+    if case.anisotropic:
+        return {f"length_scale{i}": v * factor for i, v in enumerate(case.length_scale)}
+    return {"length_scale": case.length_scale * factor}
+
+
+def _targets(case, data):
+    return data["train_y"] if case.r > 1 else data["train_y"][:, 0]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_nn_wrapper(case):
+    from muygpys_b200.neighbors import NN_Wrapper
+
+    g = load_golden(case.name)
+    data = make_data(case)
+    nbrs = NN_Wrapper(data["train_x"], case.k, nn_method="exact", algorithm="ball_tree")
+    assert (nbrs.train_count, nbrs.feature_count, nbrs.nn_count) == (case.n, case.d, case.k)
+    idx, d2 = nbrs.get_nns(data["test_x"])
+    assert isinstance(idx, np.ndarray) and idx.dtype == np.int64 and d2.dtype == np.float64
+    np.testing.assert_array_equal(idx, g["test_nn_idx"])
+    assert_close(d2, g["test_nn_d2"], 1e-12)
+    if case.batch:
+        bidx, bd2 = nbrs.get_batch_nns(data["batch_idx"])
+        np.testing.assert_array_equal(bidx, g["batch_nn_idx"])
+        assert_close(bd2, g["batch_nn_d2"], 1e-12)
+    # device tensors in -> device tensors out
+    tidx, _ = nbrs.get_nns(torch.as_tensor(data["test_x"]).cuda())
+    assert tidx.is_cuda and tidx.dtype == torch.int64
+    with pytest.raises(NotImplementedError):
+        NN_Wrapper(data["train_x"], case.k, nn_method="hnsw")
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_staged_and_fused_regression(case):
+    from muygpys_b200.examples.from_indices import (posterior_mean_from_indices,
+                                                    posterior_variance_from_indices,
+                                                    regress_from_indices,
+                                                    tensors_from_indices)
+
+    m = _mods()
+    g = load_golden(case.name)
+    data = make_data(case)
+    nn = g["test_nn_idx"]
+    targets = _targets(case, data)
+    noise = (m["HeteroscedasticNoise"](data["hetero_train_noise"][nn]) if case.hetero
+             else m["HomoscedasticNoise"](case.noise))
+    scale = m["FixedScale"]()
+    scale._set(float(g["scale_val"]))
+    muygps = build_model(case, noise=noise, scale=scale)
+    t_idx = np.arange(case.t)
+    # staged: tensors -> kernel -> posterior_mean / posterior_variance
+    Kin, Kcross, nn_targets = tensors_from_indices(muygps, t_idx, nn, data["test_x"],
+                                                   data["train_x"], targets)
+    rows = g["stage_Kin"].shape[0]
+    assert_close(Kin[:rows], g["stage_Kin"], 1e-13, "Kin")
+    assert_close(Kcross[:rows], g["stage_Kcross"], 1e-13, "Kcross")
+    np.testing.assert_array_equal(nn_targets[:rows], g["stage_nn_targets"])
+    mean = muygps.posterior_mean(Kin, Kcross, nn_targets)
+    var = muygps.posterior_variance(Kin, Kcross)
+    assert isinstance(mean, np.ndarray)
+    assert_close(mean, g["mean"], RTOL, "staged mean")
+    assert_close(var, g["var"], RTOL, "staged var")
+    assert np.all(var > 0.0)
+    # fused: one launch, nothing materialised
+    fmean, fvar = regress_from_indices(muygps, t_idx, nn, data["test_x"], data["train_x"],
+                                       targets)
+    assert_close(fmean, g["mean"], RTOL, "fused mean")
+    assert_close(fvar, g["var"], RTOL, "fused var")
+    assert_close(posterior_mean_from_indices(muygps, t_idx, nn, data["test_x"],
+                                             data["train_x"], targets), g["mean"], RTOL)
+    assert_close(posterior_variance_from_indices(muygps, t_idx, nn, data["test_x"],
+                                                 data["train_x"], targets), g["var"], RTOL)
+    # deep copies (the optimiser makes them) keep working
+    clone = copy.deepcopy(muygps)
+    cmean, _ = regress_from_indices(clone, t_idx, nn, data["test_x"], data["train_x"], targets)
+    np.testing.assert_array_equal(cmean, fmean)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.batch], ids=lambda c: c.name)
+def test_loo_objectives_staged_and_fused(case):
+    from muygpys_b200.optimize import L_BFGS_B_optimize
+    from muygpys_b200.optimize import loss as losses
+    from muygpys_b200.optimize.objective import make_fused_loo_crossval_fn
+
+    m = _mods()
+    g = load_golden(case.name)
+    data = make_data(case)
+    targets = _targets(case, data)
+    bi, bnn = data["batch_idx"], g["batch_nn_idx"]
+    scale = m["AnalyticScale"]() if case.r == 1 else m["FixedScale"]()
+    muygps = build_model(case, opt_bounds=True, scale=scale)
+    cwd, pwd, b_t, b_nn_t = muygps.make_train_tensors(bi, bnn, data["train_x"], targets)
+    for lname in case.losses:
+        loss_fn = getattr(losses, f"{lname}_fn")
+        want = g[f"obj_{lname}"]
+        staged = L_BFGS_B_optimize.make_obj_fn(muygps, b_t, b_nn_t, cwd, pwd, loss_fn=loss_fn,
+                                               loss_kwargs=case.loss_kwargs)
+        fused = make_fused_loo_crossval_fn(muygps, loss_fn, bi, bnn, data["train_x"], targets,
+                                           loss_kwargs=case.loss_kwargs)
+        for fn, tag in ((staged, "staged"), (fused, "fused")):
+            got = [fn(**theta_kwargs(case, f)) for f in g["obj_factors"]]
+            got.append(fn(noise=case.noise * 3.0, **theta_kwargs(case, 1.0)))
+            assert all(isinstance(v, float) for v in got)
+            assert_close(np.array(got), want, RTOL, f"{tag} obj_{lname}")
+    if case.r == 1:
+        assert_close(muygps.get_opt_scale_fn()(muygps.kernel(pwd), b_nn_t),
+                     g["analytic_scale"], RTOL, "analytic scale")
+        it3 = build_model(case, scale=m["AnalyticScale"](iteration_count=3))
+        assert_close(it3.get_opt_scale_fn()(it3.kernel(pwd), b_nn_t),
+                     g["analytic_scale_it3"], RTOL, "analytic scale x3")
+        fused_scale = copy.deepcopy(muygps).fused_optimize_scale(bi, bnn, data["train_x"],
+                                                                 targets).scale()
+        assert_close(fused_scale, g["analytic_scale"], RTOL, "fused optimize_scale")
+
+
+@pytest.mark.parametrize("name", ["c1_rbf_1d", "c2_m15_2d", "c4_m25_aniso"])
+def test_lbfgsb_optimisation_recovers_reference_optimum(name):
+    from muygpys_b200.examples.from_indices import optimize_from_indices
+    from muygpys_b200.optimize import L_BFGS_B_optimize
+    from muygpys_b200.optimize.loss import mse_fn
+
+    m = _mods()
+    case = by_name(name)
+    g = load_golden(case.name)
+    data = make_data(case)
+    targets = _targets(case, data)
+    bi, bnn = data["batch_idx"], g["batch_nn_idx"]
+    muygps = build_model(case, opt_bounds=True, scale=m["AnalyticScale"]())
+    opt = optimize_from_indices(muygps, bi, bnn, data["train_x"], targets, loss_fn=mse_fn,
+                                opt_fn=L_BFGS_B_optimize)
+    names, vals, _ = opt.get_opt_params()
+    assert list(names) == [str(s) for s in g["opt_mse_names"]]
+    # finite-difference L-BFGS-B: the path amplifies 1e-12 objective differences, the
+    # optimum itself agrees far better than the optimiser's own tolerance
+    np.testing.assert_allclose(vals, g["opt_mse_vals"], rtol=2e-4)
+    opt = opt.fused_optimize_scale(bi, bnn, data["train_x"], targets)
+    np.testing.assert_allclose(opt.scale(), g["opt_mse_scale"], rtol=2e-3)
+    assert opt.scale.trained
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.fast], ids=lambda c: c.name)
+def test_fast_posterior_mean_workflow(case):
+    from muygpys_b200.examples.from_indices import fast_posterior_mean_from_indices
+    from muygpys_b200.gp.tensors import fast_nn_update, make_fast_predict_tensors
+    from muygpys_b200.neighbors import NN_Wrapper
+
+    g = load_golden(case.name)
+    data = make_data(case)
+    targets = _targets(case, data)
+    x = torch.as_tensor(data["train_x"]).cuda()
+    y = torch.as_tensor(targets).cuda()
+    nbrs = NN_Wrapper(x, case.k)
+    tr_nn, _ = nbrs.get_nns(x)
+    np.testing.assert_array_equal(tr_nn[:64].cpu().numpy(), g["fast_train_nn_idx"])
+    nn_fast = fast_nn_update(tr_nn)
+    muygps = build_model(case)
+    coeffs = muygps.fused_fast_coefficients(nn_fast, x, y)
+    assert_close(coeffs[:64].cpu().numpy(), g["fast_coeffs_head"], 1e-9, "coeffs")
+    # staged equivalent on a slice (the full (n,k,k,d) tensor is what the fused path avoids)
+    pw, nn_t = make_fast_predict_tensors(tr_nn[:64], x, y)
+    Kin = muygps.kernel(muygps.kernel.deformation.metric(pw))
+    assert_close(muygps.fast_coefficients(Kin, nn_t).cpu().numpy(), g["fast_coeffs_head"], 1e-9)
+    test_nn, _ = nbrs.get_nns(torch.as_tensor(data["test_x"]).cuda())
+    closest = test_nn[:, 0]
+    fmean = fast_posterior_mean_from_indices(muygps, torch.arange(case.t).cuda(),
+                                             nn_fast[closest], torch.as_tensor(
+                                                 data["test_x"]).cuda(), x, closest, coeffs)
+    assert_close(fmean.cpu().numpy(), g["fast_mean"], RTOL, "fast mean")
+    # staged fast mean: Kcross @ coeffs[closest]
+    cw = muygps.kernel.deformation.crosswise_tensor(
+        torch.as_tensor(data["test_x"]).cuda(), x, torch.arange(case.t).cuda(), nn_fast[closest])
+    assert_close(muygps.fast_posterior_mean(muygps.kernel(cw), coeffs[closest]).cpu().numpy(),
+                 g["fast_mean"], RTOL, "staged fast mean")
+
+
+def test_reference_error_behaviour():
+    m = _mods()
+    P = m["Parameter"]
+    with pytest.raises(ValueError, match="lesser than the optimization lower bound"):
+        P(0.001, (0.01, 1.0))
+    with pytest.raises(ValueError, match="Fixed bounds do not support string"):
+        P("sample")
+    with pytest.raises(ValueError):
+        m["HomoscedasticNoise"](1e-3, (-1.0, 1.0))
+    with pytest.raises(ValueError, match="Scale parameter must be positive"):
+        m["FixedScale"]()._set(-1.0)
+    with pytest.raises(NotImplementedError):
+        m["Matern"](smoothness=P(0.7))
+    aniso = m["Matern"](smoothness=P(1.5), deformation=m["Anisotropy"](
+        m["l2"], m["VectorParameter"](P(0.1), P(0.2), P(0.3))))
+    with pytest.raises(ValueError, match="must have final dimension size of 3"):
+        aniso(torch.zeros(4, 5, 2, dtype=torch.float64, device="cuda"))
+    muygps = m["MuyGPS"](kernel=aniso)
+    with pytest.raises(ValueError):
+        muygps.fused_regress(None, torch.zeros(4, 5, dtype=torch.int64, device="cuda"),
+                             torch.rand(4, 2, dtype=torch.float64, device="cuda"),
+                             torch.rand(9, 2, dtype=torch.float64, device="cuda"),
+                             torch.rand(9, dtype=torch.float64, device="cuda"))
+    sampled = P("log_sample", (0.01, 1.0))
+    assert 0.01 <= sampled() <= 1.0
