@@ -324,7 +324,7 @@ def run_ours(args):
         except (OSError, KeyError, ValueError):
             hbm_peak = 6650.0  # fallback stated in B200_PROFILING.md
         cores = host_cores()
-        cpu_rows = max(200, 6000 // cores)
+        cpu_rows = 20000  # ~5 s per pass on one core's share
         cpu_val, cpu_n, cpu_secs = cpu_reference(cpu_rows, cores)
         out = {
             "metric": "neighbourhoods/s (k=50 fused solve+posterior)",

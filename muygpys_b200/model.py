@@ -165,11 +165,59 @@ class MuyGPS:
             length_scale=ls if deformation.anisotropic else ls[0], noise=noise,
             scale=self.scale() if scale is None else scale, **want)
 
+    def _fused_pipelined(self, indices, nn_indices, test_features, train_features,
+                         train_targets, want_mean, want_var, chunks: int = 4):
+        """Host-resident index/feature batches: upload chunk i+1 on a side stream while
+        chunk i is in the fused kernel, so the end-to-end rate is max(PCIe, compute)."""
+        x, y = fdev(train_features), fdev(train_targets)
+        dev = x.device
+        nn_h = torch.as_tensor(nn_indices)
+        b, k = nn_h.shape
+        q_h = torch.as_tensor(test_features if test_features is not None else train_features)
+        idx_h = None if indices is None else torch.as_tensor(indices)
+        r = 1 if y.dim() == 1 else y.shape[1]
+        mean = torch.empty((b, r), dtype=torch.float64, device=dev) if want_mean else None
+        var = torch.empty((b,), dtype=torch.float64, device=dev) if want_var else None
+        main = torch.cuda.current_stream()
+        side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        for s in side:
+            s.wait_stream(main)
+        # the query points are small next to the indices: one upload, then gather by index
+        q_dev = q_h if q_h.is_cuda else q_h.to(dev, non_blocking=True)
+        side_ready = torch.cuda.Event()
+        side_ready.record(main)
+        bounds = [(c * b) // chunks for c in range(chunks + 1)]
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            if hi == lo:
+                continue
+            s = side[c % 2]
+            s.wait_event(side_ready)
+            with torch.cuda.stream(s):
+                nn_c = nn_h[lo:hi].to(dev, non_blocking=True)
+                idx_c = (torch.arange(lo, hi, device=dev) if idx_h is None
+                         else idx_h[lo:hi].to(dev, non_blocking=True))
+                self._fused(idx_c, nn_c, q_dev, x, y, want_mean=want_mean, want_var=want_var,
+                            out_mean=None if mean is None else mean[lo:hi],
+                            out_var=None if var is None else var[lo:hi])
+        for s in side:
+            main.wait_stream(s)
+        return {"mean": mean, "var": var}
+
     def fused_regress(self, indices, nn_indices, test_features, train_features, train_targets,
                       want_mean=True, want_var=True):
-        """Posterior mean and scaled variance straight from indices (one launch)."""
-        out = self._fused(indices, nn_indices, test_features, train_features, train_targets,
-                          want_mean=want_mean, want_var=want_var)
+        """Posterior mean and scaled variance straight from indices (one launch, or a
+        copy/compute pipeline when the index batch still lives in host memory)."""
+        from ._arrays import is_host
+
+        if (is_host(nn_indices) and not is_host(train_features) and not is_host(train_targets)
+                and not self.noise.heteroscedastic and len(nn_indices) >= 16384
+                and (indices is None or test_features is not None)):
+            out = self._fused_pipelined(indices, nn_indices, test_features, train_features,
+                                        train_targets, want_mean, want_var)
+        else:
+            out = self._fused(indices, nn_indices, test_features, train_features,
+                              train_targets, want_mean=want_mean, want_var=want_var)
         host = (indices, nn_indices, test_features, train_features, train_targets)
         res = []
         if want_mean:

@@ -94,6 +94,8 @@ def fused_posterior(
     want_yky: bool = False,
     want_coeffs: bool = False,
     want_status: bool = False,
+    out_mean: Optional[torch.Tensor] = None,
+    out_var: Optional[torch.Tensor] = None,
 ):
     """One launch of K1 over a batch of neighbourhoods.  Returns a dict of tensors.
 
@@ -139,9 +141,14 @@ def fused_posterior(
         noise_val = float(noise)
     out = {}
     if want_mean:
-        out["mean"] = torch.empty((b, r), dtype=f64, device=dev)
+        if out_mean is not None:  # caller-provided (b,r) slice, e.g. of a pipelined batch
+            assert out_mean.is_contiguous() and tuple(out_mean.shape) == (b, r)
+        out["mean"] = out_mean if out_mean is not None else torch.empty((b, r), dtype=f64,
+                                                                        device=dev)
     if want_var:
-        out["var"] = torch.empty((b,), dtype=f64, device=dev)
+        if out_var is not None:
+            assert out_var.is_contiguous() and tuple(out_var.shape) == (b,)
+        out["var"] = out_var if out_var is not None else torch.empty((b,), dtype=f64, device=dev)
     if want_yky:
         out["yky"] = torch.empty((b,), dtype=f64, device=dev)
     if want_coeffs:
