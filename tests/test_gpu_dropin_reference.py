@@ -1,0 +1,93 @@
+"""GPU, optional: the UNMODIFIED reference (MuyGPyS 0.9.0) with our CUDA callables
+injected through its own `_backend_*` constructor arguments, side by side with the same
+reference objects on their numpy defaults -- the pattern of the reference's
+tests/backend/torch_correctness.py.  Runs only where MuyGPyS is importable: the build
+container installs it under baseline/_ref (git-ignored; it is not part of this repo and
+nothing else depends on it)."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for extra in (os.path.join(ROOT, "oracle", "ref_shims"), os.path.join(ROOT, "baseline", "_ref")):
+    if os.path.isdir(extra) and extra not in sys.path:
+        sys.path.append(extra)
+
+MuyGPyS = pytest.importorskip("MuyGPyS", reason="reference not installed on this machine")
+
+from oracle.cases import by_name, make_data  # noqa: E402
+
+from conftest import assert_close  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(case, R):
+    """(reference on numpy defaults, reference with CUDA callables injected)."""
+    from MuyGPyS.gp import MuyGPS
+    from MuyGPyS.gp.deformation import Anisotropy, Isotropy, l2
+    from MuyGPyS.gp.hyperparameter import AnalyticScale, Parameter, VectorParameter
+    from MuyGPyS.gp.kernels import Matern
+    from MuyGPyS.gp.noise import HomoscedasticNoise
+
+    def ls():
+        if case.anisotropic:
+            return VectorParameter(*[Parameter(v, (v * 0.1, v * 10)) for v in case.length_scale])
+        return Parameter(case.length_scale, (case.length_scale * 0.1, case.length_scale * 10))
+
+    nu = {2: 1.5, 3: 2.5}[case.kernel_id]
+    Def, RDef = (Anisotropy, R.Anisotropy) if case.anisotropic else (Isotropy, R.Isotropy)
+    plain = MuyGPS(kernel=Matern(smoothness=Parameter(nu), deformation=Def(l2, ls())),
+                   noise=HomoscedasticNoise(case.noise), scale=AnalyticScale())
+    ours = R.MuyGPS(kernel=R.Matern(smoothness=Parameter(nu), deformation=RDef(R.l2, ls())),
+                    noise=R.HomoscedasticNoise(case.noise), scale=R.AnalyticScale())
+    return plain, ours
+
+
+@pytest.mark.parametrize("name", ["c2_m15_2d", "c4_m25_aniso"])
+def test_injected_reference_matches_plain_reference(name):
+    from MuyGPyS.neighbors import NN_Wrapper
+    from MuyGPyS.optimize import L_BFGS_B_optimize
+    from MuyGPyS.optimize.loss import lool_fn, mse_fn
+
+    from muygpys_b200.inject import reference_objects
+    from muygpys_b200.neighbors import NN_Wrapper as GpuNN
+
+    R = reference_objects()
+    case = by_name(name)
+    data = make_data(case)
+    x, y, q = data["train_x"], data["train_y"][:, 0], data["test_x"]
+    plain, ours = _models(case, R)
+    nn_ref, d_ref = NN_Wrapper(x, case.k, nn_method="exact", algorithm="ball_tree").get_nns(q)
+    nn_gpu, d_gpu = GpuNN(x, case.k).get_nns(q)
+    np.testing.assert_array_equal(nn_gpu, nn_ref)
+    assert_close(d_gpu, d_ref, 1e-12)
+    t_idx = np.arange(case.t)
+    outs = []
+    for model in (plain, ours):
+        cw, pw, nn_t = model.make_predict_tensors(t_idx, nn_ref, q, x, y)
+        Kin, Kcross = model.kernel(pw), model.kernel(cw)
+        outs.append((cw, pw, Kin, Kcross, model.posterior_mean(Kin, Kcross, nn_t),
+                     model.posterior_variance(Kin, Kcross)))
+    for a, b, what in zip(outs[0], outs[1], ("crosswise", "pairwise", "Kin", "Kcross", "mean",
+                                             "variance")):
+        assert isinstance(b, np.ndarray)
+        assert_close(b, a, 1e-10, what)
+    # the reference's own optimiser chassis driving our kernels through its closures
+    bi = data["batch_idx"]
+    bnn, _ = NN_Wrapper(x, case.k, nn_method="exact", algorithm="ball_tree").get_batch_nns(bi)
+    vals = []
+    for model, losses in ((plain, (mse_fn, lool_fn)), (ours, (R.mse_fn, R.lool_fn))):
+        cw, pw, b_t, b_nn_t = model.make_train_tensors(bi, bnn, x, y)
+        row = []
+        for lf in losses:
+            obj = L_BFGS_B_optimize.make_obj_fn(model, b_t, b_nn_t, cw, pw, loss_fn=lf)
+            kw = ({f"length_scale{i}": v * 1.3 for i, v in enumerate(case.length_scale)}
+                  if case.anisotropic else {"length_scale": case.length_scale * 1.3})
+            row.append(obj(**kw))
+        row.append(model.scale.get_opt_fn(model)(model.kernel(pw), b_nn_t))
+        vals.append(row)
+    assert_close(np.array(vals[1]), np.array(vals[0]), 1e-10, "objectives and scale")
