@@ -26,6 +26,19 @@ from .hyperparameter import AnalyticScale, FixedScale, ScaleFn
 from .noise import HomoscedasticNoise, NoiseFn
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev: torch.device):
+    """Two long-lived copy/compute streams per device.  They are created once so that the
+    caching allocator's per-stream pools are reused from call to call (fresh streams would
+    force a cudaMalloc for every chunk)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    return _SIDE_STREAMS[key]
+
+
 def _squeeze_response(mean: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
     """(b,r) -> (b,) when the caller's targets carry no response axis."""
     return mean[:, 0] if targets.dim() == 1 else mean
@@ -179,7 +192,7 @@ class MuyGPS:
         mean = torch.empty((b, r), dtype=torch.float64, device=dev) if want_mean else None
         var = torch.empty((b,), dtype=torch.float64, device=dev) if want_var else None
         main = torch.cuda.current_stream()
-        side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        side = _side_streams(dev)
         for s in side:
             s.wait_stream(main)
         # the query points are small next to the indices: one upload, then gather by index
