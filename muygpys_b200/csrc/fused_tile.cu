@@ -62,27 +62,25 @@ __device__ __forceinline__ double rsqrt_fast(double p) {
   return fma(r, v, r);
 }
 
-// sqrt(x) for x >= 0 (0 -> 0)
+// sqrt(x) for x >= 0 (0 and denormals -> 0); the range test is an integer compare on the
+// high word so it stays off the FP64 pipe
 __device__ __forceinline__ double sqrt_fast(double x) {
   const double r = rsqrt_seed(x);
   const double g = x * r;
   const double e = fma(-g, r, 1.0);
   const double v = e * fma(e, 0.375, 0.5);
   const double s = fma(g, v, g);
-  return (x > 1e-290) ? s : 0.0;
+  return (__double2hiint(x) > 0x03c00000) ? s : 0.0;
 }
 
 // exp(-s), s >= 0: 64-entry table of 2^(j/64) + degree-5 polynomial.
 // |abs error| <= ~2.3e-16 (validated against long double on the host).
 __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ tab64) {
-  const double LOG2E = 1.4426950408889634;
-  const double MAGIC = 105553116266496.0;  // 1.5 * 2^46: ulp = 2^-6
-  const double t = fma(s, -LOG2E, MAGIC);
+  const double t = fma(s, -1.4426950408889634, 105553116266496.0);
   const int ki = __double2loint(t);
-  const double tr = t - MAGIC;
-  const double g = fma(s, -LOG2E, -tr);
-  double p = 0.0013333558146428443;
-  p = fma(g, p, 0.009618129107628477);
+  const double tr = t - 105553116266496.0;
+  const double g = fma(s, -1.4426950408889634, -tr);
+  double p = fma(g, 0.0013333558146428443, 0.009618129107628477);
   p = fma(g, p, 0.05550410866482158);
   p = fma(g, p, 0.2402265069591007);
   p = fma(g, p, 0.6931471805599453);
@@ -90,7 +88,7 @@ __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ t
   const double res = tab64[ki & (EXP_TABLE - 1)] * p;
   const int n = ki >> 6;
   const double out = __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
-  return (s < 700.0) ? out : 0.0;
+  return (__double2hiint(s) < 0x4085e000) ? out : 0.0;  // s < 700
 }
 
 struct TileArgs {
@@ -125,30 +123,31 @@ enum Formula {
   F_F2_ANY = 5   // any other kernel fed the squared metric: argument post_scale*u2
 };
 
+// NEGATED covariance (the tile image holds N = -A)
 template <int F>
-__device__ __forceinline__ double cov_from_u2(double u2, const double* tab64, double post_scale,
-                                              int kernel_id) {
-  if (F == F_M05) return exp_neg(sqrt_fast(u2), tab64);
+__device__ __forceinline__ double neg_cov(double u2, const double* tab64, double post_scale,
+                                          int kernel_id) {
+  if (F == F_M05) return -exp_neg(sqrt_fast(u2), tab64);
   if (F == F_M15) {
     const double s = sqrt_fast(u2);
-    return (1.0 + s) * exp_neg(s, tab64);
+    return (-1.0 - s) * exp_neg(s, tab64);
   }
   if (F == F_M25) {
     const double s = sqrt_fast(u2);
-    return fma(u2, 1.0 / 3.0, 1.0 + s) * exp_neg(s, tab64);
+    return fma(u2, -(1.0 / 3.0), -1.0 - s) * exp_neg(s, tab64);
   }
-  if (F == F_GAUSS) return exp_neg(0.5 * u2, tab64);
-  if (F == F_RBF_L2) return exp_neg(0.5 * sqrt_fast(u2), tab64);
+  if (F == F_GAUSS) return -exp_neg(0.5 * u2, tab64);
+  if (F == F_RBF_L2) return -exp_neg(0.5 * sqrt_fast(u2), tab64);
   const double s = post_scale * u2;
   switch (kernel_id) {
     case MGP_KERNEL_MATERN_05:
-      return exp_neg(s, tab64);
+      return -exp_neg(s, tab64);
     case MGP_KERNEL_MATERN_15:
-      return (1.0 + s) * exp_neg(s, tab64);
+      return (-1.0 - s) * exp_neg(s, tab64);
     case MGP_KERNEL_MATERN_25:
-      return fma(s * s, 1.0 / 3.0, 1.0 + s) * exp_neg(s, tab64);
+      return fma(s * s, -(1.0 / 3.0), -1.0 - s) * exp_neg(s, tab64);
     default:  // Matern inf on the squared metric
-      return exp_neg(0.5 * s * s, tab64);
+      return -exp_neg(0.5 * s * s, tab64);
   }
 }
 
@@ -190,15 +189,15 @@ __device__ __noinline__ void assemble(double* __restrict__ tiles, const double* 
     const unsigned p0 = etab[e], p1 = etab[e + 32];
     const double u0 = sqdist<D>(pts, (p0 >> 8) & 255, p0 & 255, d);
     const double u1 = sqdist<D>(pts, (p1 >> 8) & 255, p1 & 255, d);
-    const double v0 = cov_from_u2<F>(u0, tab64, post_scale, kernel_id);
-    const double v1 = cov_from_u2<F>(u1, tab64, post_scale, kernel_id);
-    tiles[p0 >> 16] = -v0;
-    tiles[p1 >> 16] = -v1;
+    const double v0 = neg_cov<F>(u0, tab64, post_scale, kernel_id);
+    const double v1 = neg_cov<F>(u1, tab64, post_scale, kernel_id);
+    tiles[p0 >> 16] = v0;
+    tiles[p1 >> 16] = v1;
   }
   if (e < n_elem) {
     const unsigned p0 = etab[e];
     const double u0 = sqdist<D>(pts, (p0 >> 8) & 255, p0 & 255, d);
-    tiles[p0 >> 16] = -cov_from_u2<F>(u0, tab64, post_scale, kernel_id);
+    tiles[p0 >> 16] = neg_cov<F>(u0, tab64, post_scale, kernel_id);
   }
 }
 

@@ -20,12 +20,14 @@ def main():
         nn = torch.randint(0, n, (b, k), device="cuda")
     torch.cuda.synchronize()
     print("knn/indices s", time.time() - t0)
-    for rep in range(3):
+    best=1e9
+    for rep in range(int(os.environ.get('REPS',12))):
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         out = ops.fused_posterior(x, q, None, nn, y, kernel_id=kid, metric_id=0, length_scale=0.1,
                                   noise=1e-3)
         e.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(e)
-        print(json.dumps({"ms": ms, "nbhd_per_s": b / ms * 1e3}))
+        best=min(best,ms)
+    print(json.dumps({"best_ms": best, "nbhd_per_s": b / best * 1e3}))
 main()
