@@ -124,8 +124,9 @@ const char* mgp_last_error(void);
 size_t mgp_fused_workspace_bytes(const mgp_problem* p);
 int mgp_fused_posterior(const mgp_problem* p, void* ws, size_t ws_bytes, void* stream);
 
-/* Test/bench hook: 0 = choose automatically, 1 = always the generic shared-memory
- * kernel, 2 = the register-tile DMMA kernel where supported.  Lets the two
+/* Test/bench hook: 0 = choose automatically (pipelined tile > tile > generic), 1 = always
+ * the generic shared-memory kernel, 2 = the register-tile DMMA kernel where supported,
+ * 3 = the software-pipelined tile kernel (error if the shape is unsupported).  Lets the
  * independently written variants be cross-checked on identical inputs. */
 int mgp_set_fused_variant(int32_t variant);
 

@@ -188,6 +188,9 @@ static int launch_generic(const mgp_problem* p, const Model& model, cudaStream_t
   return check_launch("fused_generic_kernel");
 }
 
+int fused_variant();
+int fused_pipe_supported(const mgp_problem* p, const Model& model);
+int launch_fused_pipe(const mgp_problem* p, const Model& model, cudaStream_t stream);
 int fused_tile_supported(const mgp_problem* p, const Model& model);
 int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t ws_bytes,
                       cudaStream_t stream);
@@ -222,6 +225,13 @@ extern "C" int mgp_fused_posterior(const mgp_problem* p, void* ws, size_t ws_byt
                        &model);
   if (rc != MGP_OK) return rc;
   if (p->b == 0) return MGP_OK;
+  const int variant = mgp::fused_variant();
+  if ((variant == 0 || variant == 3) && mgp::fused_pipe_supported(p, model))
+    return mgp::launch_fused_pipe(p, model, (cudaStream_t)stream);
+  if (variant == 3) {
+    mgp::set_error("the pipelined tile kernel does not support this shape");
+    return MGP_ERR_UNSUPPORTED;
+  }
   if (mgp::fused_tile_supported(p, model))
     return mgp::launch_fused_tile(p, model, ws, ws_bytes, (cudaStream_t)stream);
   return mgp::launch_generic(p, model, (cudaStream_t)stream);

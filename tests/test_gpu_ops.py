@@ -30,14 +30,15 @@ def _2d(x):
     return x[:, None] if x.ndim == 1 else x
 
 
-@pytest.fixture(scope="module", params=["auto", "generic"])
+@pytest.fixture(scope="module", params=["auto", "tile", "generic"])
 def ops(request):
-    """Every test runs twice: through the automatically chosen fused kernel (the
-    register-tile DMMA variant where the shape allows) and through the generic
-    shared-memory variant, two independently written implementations."""
+    """Every test runs three times: through the automatically chosen fused kernel (the
+    software-pipelined tile kernel where the shape allows, else the tile kernel), with the
+    pipelined variant disabled, and through the generic shared-memory kernel -- independently
+    written implementations of the same contract."""
     from muygpys_b200 import ops as _ops
 
-    _ops.set_fused_variant(0 if request.param == "auto" else 1)
+    _ops.set_fused_variant({"auto": 0, "tile": 2, "generic": 1}[request.param])
     yield _ops
     _ops.set_fused_variant(0)
 

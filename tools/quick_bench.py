@@ -21,6 +21,7 @@ def main():
     torch.cuda.synchronize()
     print("knn/indices s", time.time() - t0)
     best=1e9
+    ops.set_fused_variant(int(os.environ.get('VARIANT',0)))
     for rep in range(int(os.environ.get('REPS',12))):
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
