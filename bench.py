@@ -226,10 +226,19 @@ def run_ours(args):
     x_h, y_h, _ = make_data(2)                       # same training set on every rank
     q_h = np.random.default_rng(1000 + rank).uniform(size=(N_TEST, D))
     x, y, q = (torch.as_tensor(a).to(dev) for a in (x_h, y_h, q_h))
+    from muygpys_b200.neighbors import NN_Wrapper
+
     t0 = time.perf_counter()
-    nn, _ = ops.knn(x, q, K)
+    nbrs = NN_Wrapper(x, K)  # uniform-grid exact KNN index (d = 2), training set resident
     torch.cuda.synchronize()
-    knn_s = time.perf_counter() - t0
+    knn_build_s = time.perf_counter() - t0
+    nn, _ = nbrs.get_nns(q)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        nn, _ = nbrs.get_nns(q)
+    torch.cuda.synchronize()
+    knn_s = (time.perf_counter() - t0) / 5
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     model = MuyGPS(kernel=Matern(smoothness=Parameter(1.5),
                                  deformation=Isotropy(l2, Parameter(LENGTH_SCALE, (0.01, 1.0)))),
@@ -288,8 +297,7 @@ def run_ours(args):
     # ---- LOO-mse objective evaluations (second half of the BASELINE metric) -----------
     bi = torch.as_tensor(np.random.default_rng(50 + rank).choice(N_TRAIN, LOO_BATCH,
                                                                  replace=False)).to(dev)
-    bnn, _ = ops.knn(x, x[bi], K + 1)
-    bnn = bnn[:, 1:].contiguous()
+    bnn, _ = nbrs.get_batch_nns(bi)
     obj = make_fused_loo_crossval_fn(model, mse_fn, bi, bnn, x, y, distributed=world > 1)
     for _ in range(3):
         obj(length_scale=0.1)
@@ -335,7 +343,7 @@ def run_ours(args):
                 "workload": "C2: 2-D spatial, 1M train / 100k test per GPU, Matern nu=3/2 "
                             "Isotropy(l2, 0.1), k=50, tau^2=1e-3, posterior mean+variance",
                 "neighbours": "exact KNN precomputed on device, not timed",
-                "knn_seconds_100k_queries": knn_s,
+                "knn_seconds_100k_queries": knn_s, "knn_index_build_seconds": knn_build_s,
                 "l2": "256 MB flush between timed steps",
                 "parallelism": f"dp{world}: test rows sharded, training set replicated"},
             "e2e": {"value": world * N_TEST / (e2e_ms_per_step * 1e-3),

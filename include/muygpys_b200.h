@@ -152,6 +152,21 @@ int mgp_knn(const double* train, int64_t n, const double* queries, int64_t q, in
             int32_t k, int32_t exclude_self, const int64_t* self_idx, int64_t* out_idx,
             double* out_d2, void* ws, size_t ws_bytes, void* stream);
 
+/* Uniform-grid variant for d <= 3 (same results, bit for bit, as mgp_knn).
+ * mgp_knn_grid_cells writes the cell id of every point (cells of edge `cell_size`, `dims[d]`
+ * cells per axis starting at `origin[d]`; dims/origin are HOST arrays).  The caller sorts the
+ * training points by cell id (any device sort) and passes the sorted points, their original
+ * rows and the (ncells+1) cell offsets to mgp_knn_grid_query.  `query_order` (nullable) is the
+ * order in which queries are processed (sorted by cell for coherent loads); outputs are always
+ * written at the query's own row.  `self_idx` (nullable) as in mgp_knn. */
+int mgp_knn_grid_cells(const double* points, int64_t n, int32_t d, const int32_t* dims,
+                       const double* origin, double cell_size, int32_t* out_cell, void* stream);
+int mgp_knn_grid_query(const double* sorted_points, const int32_t* sorted_ids,
+                       const int32_t* cell_start, int64_t n, int32_t d, const int32_t* dims,
+                       const double* origin, double cell_size, const double* queries,
+                       const int32_t* query_order, int64_t q, int32_t k, const int64_t* self_idx,
+                       int64_t* out_idx, double* out_d2, void* stream);
+
 /* ---- fast posterior mean apply (a12, K4): crosswise + kernel + dot ------
  * mean[i,:] = sum_j kernel(dist(query[i], train[nn_idx[i,j]])) * coeffs[coeff_row[i], j, :]
  * Replaces fast_posterior_mean_from_indices        S/examples/from_indices.py:93-123 */

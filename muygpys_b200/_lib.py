@@ -64,6 +64,9 @@ SIGNATURES = {
                                     _sz, _dp]),
     "mgp_knn_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "mgp_knn": (C.c_int, [_dp, _i64, _dp, _i64, _i32, _i32, _i32, _dp, _dp, _dp, _dp, _sz, _dp]),
+    "mgp_knn_grid_cells": (C.c_int, [_dp, _i64, _i32, C.POINTER(C.c_int32), _HOSTD, _f64, _dp, _dp]),
+    "mgp_knn_grid_query": (C.c_int, [_dp, _dp, _dp, _i64, _i32, C.POINTER(C.c_int32), _HOSTD, _f64,
+                                     _dp, _dp, _i64, _i32, _dp, _dp, _dp, _dp]),
     "mgp_fast_mean": (C.c_int, [_PP, _dp, _dp, _dp]),
     "mgp_crosswise_diffs": (C.c_int, [_dp, _dp, _dp, _dp, _i64, _i32, _i32, _dp, _dp]),
     "mgp_pairwise_diffs": (C.c_int, [_dp, _dp, _i64, _i32, _i32, _dp, _dp]),

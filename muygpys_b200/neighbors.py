@@ -37,12 +37,22 @@ class NN_Wrapper:
         # sklearn returns unsquared distances for metric="euclidean"; the
         # reference only squares for minkowski/p=2 (S/neighbors.py:246-250)
         self._squared = metric == "minkowski"
+        # d <= 3: exact search on a uniform cell grid (bit-identical to brute force, orders of
+        # magnitude fewer distance evaluations); otherwise brute force.  `algorithm="brute"`
+        # (a sklearn keyword the reference forwards) forces the brute-force kernel.
+        self._grid = None
+        if (self.feature_count <= 3 and self.train_count >= 64
+                and kwargs.get("algorithm", "auto") != "brute"):
+            self._grid = ops.KnnGrid(self.train)
 
     def _query(self, samples, k: int):
         s = fdev(samples)
         if s.dim() == 1:
             s = s[:, None]
-        idx, d2 = ops.knn(self.train, s, k)
+        if self._grid is not None:
+            idx, d2 = self._grid.query(s, k)
+        else:
+            idx, d2 = ops.knn(self.train, s, k)
         if not self._squared:
             d2 = d2.sqrt()
         return idx, d2

@@ -252,6 +252,74 @@ def knn(train, queries, k, self_idx=None):
     return out_idx, out_d2
 
 
+class KnnGrid:
+    """Uniform cell grid over a low-dimensional training set (d <= 3) for exact KNN.
+
+    Built once per training set: cell ids from the CUDA kernel, a device radix sort
+    (torch.sort, plumbing) to bucket the points, and the per-cell offsets."""
+
+    POINTS_PER_CELL = 12.0
+    MAX_CELLS = 1 << 27
+
+    def __init__(self, train: torch.Tensor):
+        lib = L.lib()
+        train = as_2d(fdev(train, "train"))
+        n, d = train.shape
+        if not 1 <= d <= 3:
+            raise NotImplementedError("the grid index supports 1 <= d <= 3")
+        self.n, self.d = n, d
+        lo = train.min(dim=0).values
+        hi = train.max(dim=0).values
+        extent = (hi - lo).clamp_min(0.0).cpu().tolist()
+        span = [e for e in extent if e > 0.0]
+        cells = min(max(n / self.POINTS_PER_CELL, 1.0), float(self.MAX_CELLS))
+        if span:
+            volume = 1.0
+            for e in span:
+                volume *= e
+            h = (volume / cells) ** (1.0 / len(span))
+        else:
+            h = 1.0
+        self.h = float(h)
+        self.dims = [max(1, int(e / self.h) + 1) for e in extent]
+        self.origin = [float(v) for v in lo.cpu().tolist()]
+        self._dims_c = (C.c_int32 * d)(*self.dims)
+        self._origin_c = (C.c_double * d)(*self.origin)
+        ncells = 1
+        for v in self.dims:
+            ncells *= v
+        cell = torch.empty((n,), dtype=torch.int32, device=train.device)
+        L.check(lib.mgp_knn_grid_cells(_p(train), n, d, self._dims_c, self._origin_c, self.h,
+                                       _p(cell), _stream()))
+        sorted_cell, perm = torch.sort(cell)
+        self.sorted_points = train[perm].contiguous()
+        self.sorted_ids = perm.to(torch.int32).contiguous()
+        edges = torch.arange(ncells + 1, dtype=torch.int32, device=train.device)
+        self.cell_start = torch.searchsorted(sorted_cell, edges).to(torch.int32).contiguous()
+
+    def query(self, queries: torch.Tensor, k: int, self_idx=None):
+        lib = L.lib()
+        queries = as_2d(fdev(queries, "queries"))
+        q, d = queries.shape
+        if d != self.d:
+            raise ValueError(f"query feature count {d} != train feature count {self.d}")
+        dev = queries.device
+        out_idx = torch.empty((q, k), dtype=i64, device=dev)
+        out_d2 = torch.empty((q, k), dtype=f64, device=dev)
+        order = None
+        if q > 1:
+            qcell = torch.empty((q,), dtype=torch.int32, device=dev)
+            L.check(lib.mgp_knn_grid_cells(_p(queries), q, d, self._dims_c, self._origin_c,
+                                           self.h, _p(qcell), _stream()))
+            order = torch.argsort(qcell).to(torch.int32).contiguous()
+        self_idx = None if self_idx is None else idev(self_idx)
+        L.check(lib.mgp_knn_grid_query(_p(self.sorted_points), _p(self.sorted_ids),
+                                       _p(self.cell_start), self.n, d, self._dims_c,
+                                       self._origin_c, self.h, _p(queries), _p(order), q, int(k),
+                                       _p(self_idx), _p(out_idx), _p(out_d2), _stream()))
+        return out_idx, out_d2
+
+
 # --------------------------------------------------------------------------
 # staged ops
 # --------------------------------------------------------------------------

@@ -39,6 +39,24 @@ def c2():
     return dict(x=x, q=q, y=y, xd=xd, qd=qd, yd=yd, nn=nn, d2=d2, rng=rng)
 
 
+def test_c2_grid_knn_equals_brute_force(c2):
+    """1 M train / 100 k queries: the grid search returns the brute-force result exactly."""
+    import time
+
+    from muygpys_b200 import ops
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    grid = ops.KnnGrid(c2["xd"])
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    gi, gd = grid.query(c2["qd"], 50)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"grid build {t1 - t0:.3f} s, 100k queries {t2 - t1:.4f} s")
+    assert torch.equal(gi, c2["nn"]) and torch.equal(gd, c2["d2"])
+
+
 def test_c2_knn_properties(c2):
     nn, d2 = c2["nn"].cpu().numpy(), c2["d2"].cpu().numpy()
     assert nn.shape == (100_000, 50) and nn.dtype == np.int64

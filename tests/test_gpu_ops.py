@@ -238,3 +238,45 @@ def test_error_behaviour(ops):
     out = ops.fused_posterior(x, x, None, dup, y, kernel_id=2, metric_id=0, length_scale=0.1,
                               noise=0.0, want_status=True)
     assert int(out["status"][0]) == 1 and torch.isnan(out["var"][0])
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("layout", ["uniform", "clustered", "lattice"])
+def test_grid_knn_equals_brute_force_bit_for_bit(d, layout):
+    """The uniform-grid search (d <= 3) must return exactly what the brute-force kernel
+    returns: same indices (ties resolved to the lower train row) and the same bits of
+    squared distance -- on uniform data, strongly clustered data and an integer lattice
+    where almost every distance is tied."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(100 * d + len(layout))
+    n, q, k = 20_000, 3_000, 37
+    if layout == "uniform":
+        x = rng.uniform(size=(n, d))
+        qs = rng.uniform(-0.1, 1.1, size=(q, d))  # some queries outside the bounding box
+    elif layout == "clustered":
+        centers = rng.uniform(size=(5, d))
+        x = centers[rng.integers(0, 5, n)] + 1e-3 * rng.normal(size=(n, d))
+        x[:50] = rng.uniform(-3, 3, size=(50, d))  # a few far outliers stretch the grid
+        qs = centers[rng.integers(0, 5, q)] + 2e-3 * rng.normal(size=(q, d))
+    else:
+        side = int(round(n ** (1.0 / d))) + 1
+        x = rng.integers(0, side, size=(n, d)).astype(np.float64)  # duplicates and ties
+        qs = rng.integers(0, side, size=(q, d)).astype(np.float64)
+    xd, qd = dev(x), dev(qs)
+    grid = ops.KnnGrid(xd)
+    gi, gd = grid.query(qd, k)
+    bi, bd = ops.knn(xd, qd, k)
+    assert torch.equal(gi, bi) and torch.equal(gd, bd)
+    # self-exclusion and the reference's k+1-and-drop both agree with brute force too
+    rows = dev(rng.choice(n, 500, replace=False))
+    gi2, gd2 = grid.query(xd[rows], k, self_idx=rows)
+    bi2, bd2 = ops.knn(xd, xd[rows], k, self_idx=rows)
+    assert torch.equal(gi2, bi2) and torch.equal(gd2, bd2)
+    gi3, _ = grid.query(xd[rows], k + 1)
+    bi3, _ = ops.knn(xd, xd[rows], k + 1)
+    assert torch.equal(gi3, bi3)
+    # a single query and k = 1
+    g1, _ = grid.query(qd[:1], 1)
+    b1, _ = ops.knn(xd, qd[:1], 1)
+    assert torch.equal(g1, b1)
