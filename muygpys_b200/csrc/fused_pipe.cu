@@ -305,7 +305,11 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
                                                double& c_last0, double& c_last1) {
   constexpr int JE = (KP + 7) / 8;
   constexpr int ZF = (KP - 3) >> 3;
+#ifdef MGP_DEBUG_SKIP_EVAL
+  constexpr int CI_ = 0;
+#else
   constexpr int CI_ = (J < JE) ? chunk_iters<KP>(J) : 0;
+#endif
   constexpr int CB_ = chunk_begin<KP>(J < JE ? J : 0);
   constexpr int NC_ = (KP - 8 * J) >= 8 ? 8 : ((KP - 8 * J) > 0 ? (KP - 8 * J) : 1);
   constexpr int ncols = (J < JE) ? NC_ : 0;
@@ -351,7 +355,11 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
     c[I][0] = -c[I][0];
     c[I][1] = -c[I][1];
   }
+#ifdef MGP_DEBUG_SKIP_CHAIN
+  if (false) {
+#else
   if (J < JE) {
+#endif
     // in-tile LDL^T on the diagonal tile and on an identity tile (-> M), with the next
     // neighbourhood's element evaluations woven into the column steps
     double v0 = (rho == 2 * q) ? 1.0 : 0.0, v1 = (rho == 2 * q + 1) ? 1.0 : 0.0;
@@ -403,7 +411,6 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
   static_assert((KP >> 3) == T - 1, "Schur block must live in the last tile");
   static_assert(LI + 1 < 8, "target row must live in the last tile");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rho = lane >> 2, q = lane & 3;
   const int k = a.k;
 
   double* tab64 = smem;
@@ -441,7 +448,6 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
   const long long wglobal = (long long)blockIdx.x * PIPE_WARPS + warp;
   const long long wstride = (long long)gridDim.x * PIPE_WARPS;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  const int qb = lane & ~3;
   const double cs0 = a.coord_scale[0], cs1 = a.coord_scale[1];
   const double noise = a.noise;
 
