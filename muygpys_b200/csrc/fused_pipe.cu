@@ -331,6 +331,8 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
 #pragma unroll
   for (int I = (ZF > J ? ZF : J); I < T; ++I)
     *reinterpret_cast<double2*>(tiles + tile_base(I, J) + 2 * lane) = make_double2(0.0, 0.0);
+  if (J < ZF)  // keep the never-assembled upper half of the diagonal tile finite (0 * NaN)
+    *reinterpret_cast<double2*>(tiles + tile_base(J, J) + 2 * lane) = make_double2(0.0, 0.0);
   __syncwarp();
   // ---- next neighbourhood: padding / target cells of its tile column J ------------------
   if (lane < 8) {
@@ -500,6 +502,8 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
   scale_pts(0);
   for (int e = lane; e < (NT * 64 - tile_base(ZF, 0)) / 2; e += 32)
     reinterpret_cast<double2*>(tiles + tile_base(ZF, 0))[e] = make_double2(0.0, 0.0);
+  for (int J = 0; J < ZF; ++J)
+    reinterpret_cast<double2*>(tiles + tile_base(J, J))[lane] = make_double2(0.0, 0.0);
   __syncwarp();
   for (int J = 0; J < T; ++J) specials(J, ys_buf);
   assemble_flat<F>(tiles, reinterpret_cast<const double2*>(pts_buf), etab, tab64, ROWS, lane,

@@ -82,8 +82,12 @@ __device__ __forceinline__ void assemble_any(int formula, double* tiles, const d
 }
 
 
-template <int T>
-__global__ void __launch_bounds__(TILE_WARPS * 32, 3)
+// SMEM_L = false: finished tiles live in registers (T <= 7, three CTAs per SM).
+// SMEM_L = true : finished tiles are written back over their own cells of the shared-memory
+//                 image and re-read as DMMA fragments (one LDS.128 per tile per use), which
+//                 takes T up to 13 (k ~ 100, BASELINE config C4) at one CTA per SM.
+template <int T, bool SMEM_L>
+__global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
     fused_tile_kernel(const TileArgs a, size_t warp_doubles) {
   extern __shared__ double smem[];
   constexpr int NT = T * (T + 1) / 2;
@@ -122,8 +126,9 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
   }
   __syncthreads();
 
-  const long long wglobal = (long long)blockIdx.x * TILE_WARPS + warp;
-  const long long wstride = (long long)gridDim.x * TILE_WARPS;
+  const int nwarps = blockDim.x >> 5;
+  const long long wglobal = (long long)blockIdx.x * nwarps + warp;
+  const long long wstride = (long long)gridDim.x * nwarps;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   const int qb = lane & ~3;
   const int zero_from = (k >> 3);  // first tile row that holds padding / augmented rows
@@ -146,12 +151,17 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
       for (int c = 0; c < r; ++c) cp_async8(dy + c, py + c);
     }
   };
-  long long src0 = load_src(wglobal, lane), src1 = load_src(wglobal, lane + 32);
-  issue_rows(0, lane, src0);
-  issue_rows(0, lane + 32, src1);
+  // lane l stages points l, l+32, ... (NS = 2 covers k <= 63, NS = 4 covers k <= 127)
+  constexpr int NS = (T <= 7) ? 2 : 4;
+  long long src[NS];
+#pragma unroll
+  for (int m = 0; m < NS; ++m) {
+    src[m] = load_src(wglobal, lane + 32 * m);
+    issue_rows(0, lane + 32 * m, src[m]);
+  }
   cp_async_commit();
-  src0 = load_src(wglobal + wstride, lane);
-  src1 = load_src(wglobal + wstride, lane + 32);
+#pragma unroll
+  for (int m = 0; m < NS; ++m) src[m] = load_src(wglobal + wstride, lane + 32 * m);
   int buf = 0;
 
   for (long long row = wglobal; row < a.b; row += wstride, buf ^= 1) {
@@ -160,15 +170,21 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
       double2* z = reinterpret_cast<double2*>(tiles + tile_base(zero_from, 0));
       const int cnt = (NT * 64 - tile_base(zero_from, 0)) / 2;
       for (int e = lane; e < cnt; e += 32) z[e] = make_double2(0.0, 0.0);
+      // The strictly upper halves of the diagonal tiles are never assembled; they only ever
+      // feed other upper cells, but a stale NaN there would leak into finished entries
+      // through 0 * NaN in the masked column updates, so keep them finite.
+#pragma unroll
+      for (int J = 0; J < T; ++J)
+        reinterpret_cast<double2*>(tiles + tile_base(J, J))[lane] = make_double2(0.0, 0.0);
     }
     cp_async_wait_all();
     __syncwarp();
     // rows of the next neighbourhood start flowing in; its successor's indices follow
-    issue_rows(buf ^ 1, lane, src0);
-    issue_rows(buf ^ 1, lane + 32, src1);
+#pragma unroll
+    for (int m = 0; m < NS; ++m) issue_rows(buf ^ 1, lane + 32 * m, src[m]);
     cp_async_commit();
-    src0 = load_src(row + 2 * wstride, lane);
-    src1 = load_src(row + 2 * wstride, lane + 32);
+#pragma unroll
+    for (int m = 0; m < NS; ++m) src[m] = load_src(row + 2 * wstride, lane + 32 * m);
     double* pts = pts_buf + buf * pts_doubles;
     const double* ys = ys_buf + buf * ys_doubles;
     // fold the length scale(s) into the staged coordinates; scatter -y into rows kp+1+c
@@ -196,7 +212,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
     // fragment is the 8x4 slice of the EVEN columns {0,2,4,6}, register 1 the slice
     // of the odd columns; the contraction index of U_I D^-1 U_J^T may be visited in
     // any order, so two DMMAs (even, odd) update a tile with no re-layout at all.
-    double l0[T][T], l1[T][T];  // [I][P], I > P
+    double l0[SMEM_L ? 1 : T][SMEM_L ? 1 : T], l1[SMEM_L ? 1 : T][SMEM_L ? 1 : T];  // [I][P]
     double dinv0[T], dinv1[T];  // 1/d for this lane's two columns of tile column P
     bool ok = true;
 #pragma unroll
@@ -212,11 +228,24 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
 #pragma unroll
       for (int P = 0; P < J; ++P) {
         if (8 * P < kp) {  // tile column P carries eliminated columns
-          const double b0 = l0[J][P] * dinv0[P], b1 = l1[J][P] * dinv1[P];
+          if (SMEM_L) {
+            const double2 lj = *reinterpret_cast<const double2*>(tiles + tile_base(J, P) +
+                                                                 rho * 8 + 2 * q);
+            const double b0 = lj.x * dinv0[P], b1 = lj.y * dinv1[P];
 #pragma unroll
-          for (int I = J; I < T; ++I) {
-            dmma_acc(c[I][0], c[I][1], l0[I][P], b0);
-            dmma_acc(c[I][0], c[I][1], l1[I][P], b1);
+            for (int I = J; I < T; ++I) {
+              const double2 li = *reinterpret_cast<const double2*>(tiles + tile_base(I, P) +
+                                                                   rho * 8 + 2 * q);
+              dmma_acc(c[I][0], c[I][1], li.x, b0);
+              dmma_acc(c[I][0], c[I][1], li.y, b1);
+            }
+          } else {
+            const double b0 = l0[J][P] * dinv0[P], b1 = l1[J][P] * dinv1[P];
+#pragma unroll
+            for (int I = J; I < T; ++I) {
+              dmma_acc(c[I][0], c[I][1], l0[I][P], b0);
+              dmma_acc(c[I][0], c[I][1], l1[I][P], b1);
+            }
           }
         }
       }
@@ -275,13 +304,15 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 3)
             dmma_acc(n0, n1, c[I][1], bm1);
             c[I][0] = n0;
             c[I][1] = n1;
-            l0[I][J] = n0;
-            l1[I][J] = n1;
+            if (!SMEM_L) {
+              l0[I][J] = n0;
+              l1[I][J] = n1;
+            }
           }
         }
       }
       // write back what later phases read from shared memory
-      if (a.coeffs || 8 * J + 8 > kp) {
+      if (SMEM_L || a.coeffs || 8 * J + 8 > kp) {
 #pragma unroll
         for (int I = J; I < T; ++I)
           *reinterpret_cast<double2*>(tiles + tile_base(I, J) + rho * 8 + 2 * q) =
@@ -340,8 +371,8 @@ int fused_tile_supported(const mgp_problem* p, const Model& model) {
   (void)model;
   if (g_variant == 1) return 0;
   if (p->d > TILE_MAX_D) return 0;
-  if (p->k > 255) return 0;
-  return tiles_needed(p->k, p->r) <= 7;
+  if (p->k > 127) return 0;  // the row prefetch stages at most 128 points per warp
+  return tiles_needed(p->k, p->r) <= 13;
 }
 
 int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t ws_bytes,
@@ -357,26 +388,37 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
   const size_t warp_doubles = (size_t)NT * 64 + 2 * (size_t)((((p->k + 1) * p->d) + 1) & ~1) +
                               2 * (size_t)(((p->k * p->r) + 1) & ~1);
   const size_t shared_doubles = EXP_TABLE + (size_t)((((a.n_elem + 1) / 2) + 1) & ~1);
-  const size_t smem = (shared_doubles + warp_doubles * TILE_WARPS) * sizeof(double);
+  const bool smem_l = T > 7;
+  int warps = TILE_WARPS;
+  while (warps > 1 &&
+         (shared_doubles + warp_doubles * warps) * sizeof(double) > (size_t)max_smem_optin())
+    --warps;  // large k: fewer neighbourhoods in flight per CTA
+  const size_t smem = (shared_doubles + warp_doubles * warps) * sizeof(double);
   MGP_REQUIRE(smem <= (size_t)max_smem_optin(), MGP_ERR_UNSUPPORTED,
               "tile kernel shared memory %zu too large", smem);
-  long long blocks = (p->b + TILE_WARPS - 1) / TILE_WARPS;
-  const long long cap = (long long)sm_count() * 3;
+  long long blocks = (p->b + warps - 1) / warps;
+  const long long cap = (long long)sm_count() * (smem_l ? 1 : 3);
   if (blocks > cap) blocks = cap;
-#define MGP_TILE(TT)                                                                          \
+#define MGP_TILE(TT, SL)                                                                      \
   case TT:                                                                                    \
-    cudaFuncSetAttribute(fused_tile_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                         (int)smem);                                                          \
-    fused_tile_kernel<TT><<<(unsigned)blocks, TILE_WARPS * 32, smem, stream>>>(a, warp_doubles); \
+    cudaFuncSetAttribute(fused_tile_kernel<TT, SL>,                                           \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+    fused_tile_kernel<TT, SL><<<(unsigned)blocks, warps * 32, smem, stream>>>(a, warp_doubles); \
     break;
   switch (T) {
-    MGP_TILE(1)
-    MGP_TILE(2)
-    MGP_TILE(3)
-    MGP_TILE(4)
-    MGP_TILE(5)
-    MGP_TILE(6)
-    MGP_TILE(7)
+    MGP_TILE(1, false)
+    MGP_TILE(2, false)
+    MGP_TILE(3, false)
+    MGP_TILE(4, false)
+    MGP_TILE(5, false)
+    MGP_TILE(6, false)
+    MGP_TILE(7, false)
+    MGP_TILE(8, true)
+    MGP_TILE(9, true)
+    MGP_TILE(10, true)
+    MGP_TILE(11, true)
+    MGP_TILE(12, true)
+    MGP_TILE(13, true)
     default:
       set_error("tile variant does not support %d tile rows", T);
       return MGP_ERR_UNSUPPORTED;
