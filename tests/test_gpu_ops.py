@@ -303,3 +303,28 @@ def test_fast_coefficients_reproducible_over_many_launches(ops):
         onn = torch.randint(0, 5000, (512, case.k), device="cuda")
         ops.fused_posterior(other, other, None, onn, other[:, 0].contiguous(), kernel_id=0,
                             metric_id=1, length_scale=1e-3, noise=0.0)
+
+
+def test_high_d_knn_tiled_matches_warp_kernel_and_oracle():
+    """d = 784: the register-tiled sweep (q >= 8, training set split over CTAs and merged) and
+    the warp-per-query kernel (q < 8) agree, and the tiled kernel reproduces the oracle's
+    direct-difference distances bit for bit (same feature order, no FMA)."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(784)
+    n, q, d, k = 9_000, 70, 784, 30
+    x = rng.normal(size=(n, d))
+    qs = rng.normal(size=(q, d))
+    x[17] = x[4000]  # an exact duplicate: tie must resolve to the lower row
+    xd, qd = dev(x), dev(qs)
+    ti, td = ops.knn(xd, qd, k)
+    want_i, want_d = O.knn_exact(x, qs, k, chunk=8)
+    np.testing.assert_array_equal(ti.cpu().numpy(), want_i)
+    np.testing.assert_array_equal(td.cpu().numpy(), want_d)
+    wi = torch.cat([ops.knn(xd, qd[i:i + 5], k)[0] for i in range(0, 20, 5)])
+    assert torch.equal(wi, ti[:20])
+    rows = dev(np.array([17, 4000, 5, 8999, 123, 77, 4001, 16]))
+    si, _ = ops.knn(xd, xd[rows], k, self_idx=rows)
+    s1, _ = ops.knn(xd, xd[rows], k + 1)
+    assert int(si[0, 0]) == 4000 and int(si[1, 0]) == 17  # the duplicate is the nearest other
+    assert torch.equal(s1[2:, 1:], si[2:])
