@@ -40,7 +40,7 @@ KERNEL_M15, METRIC_L2 = 2, 0
 FLOP_PER_NBHD = 62_692  # F(k=50, d=2, r=1, Matern 3/2)
 BYTES_PER_NBHD = 1_632  # B(k=50, d=2, r=1)
 LOO_BATCH = 10_000      # LOO-mse objective evaluations are timed on this batch per rank
-# dram__bytes_read.sum + dram__bytes_write.sum of fused_tile_kernel<7> for ONE launch over
+# dram__bytes_read.sum + dram__bytes_write.sum of fused_pipe_kernel<7,52,1> for ONE launch over
 # the 100 k batch, from the ncu --set full capture summarised in profiles/ (r1)
 NCU_TRAFFIC_BYTES = 68_049_152
 

@@ -40,7 +40,7 @@ __host__ __device__ constexpr int chunk_begin(int J) {
 template <int F>
 __device__ __forceinline__ void eval_entry(unsigned p, double* __restrict__ tiles,
                                            const double2* __restrict__ pts2,
-                                           const double* __restrict__ tab64, double noise) {
+                                           double tab64, double noise) {
   const int pi = (p >> 8) & 255, j = p & 255;
   const double2 a = pts2[pi], b = pts2[j];
   const double dx = a.x - b.x, dy = a.y - b.y;
@@ -56,7 +56,7 @@ template <int F>
 __device__ __forceinline__ void eval_pair(unsigned p0, unsigned p1, int dep,
                                           double* __restrict__ tiles,
                                           const double2* __restrict__ pts2,
-                                          const double* __restrict__ tab64, double noise) {
+                                          double tab64, double noise) {
   const int pi0 = (p0 >> 8) & 255, j0 = p0 & 255, pi1 = (p1 >> 8) & 255, j1 = p1 & 255;
   const double2 a0 = pts2[pi0 + dep], b0 = pts2[j0], a1 = pts2[pi1 + dep], b1 = pts2[j1];
   const double dx0 = a0.x - b0.x, dy0 = a0.y - b0.y, dx1 = a1.x - b1.x, dy1 = a1.y - b1.y;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void eval_pair(unsigned p0, unsigned p1, int dep,
 
 template <int F>
 __device__ __noinline__ void assemble_flat(double* tiles, const double2* pts2,
-                                           const unsigned* etab, const double* tab64,
+                                           const unsigned* etab, double tab64,
                                            int rows, int lane, double noise) {
   int it = 0;
   for (; it + 1 < rows; it += 2)
@@ -142,18 +142,18 @@ struct StagedEval {
   __device__ __forceinline__ void l10() {  // range reduction of exp(-s); polynomial prefactor
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      t[i] = fma(s[i], -1.4426950408889634, 105553116266496.0);
+      t[i] = fma(s[i], -1.4426950408889634, 211106232532992.0);
       if (F == F_M05) pref[i] = -1.0;
       if (F == F_M15) pref[i] = -1.0 - s[i];
       if (F == F_M25) pref[i] = fma(u[i], -(1.0 / 3.0), -1.0 - s[i]);
     }
   }
-  __device__ __forceinline__ void l11(const double* tab64) {
+  __device__ __forceinline__ void l11(double tab64) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       ki[i] = __double2loint(t[i]);
-      tabv[i] = tab64[ki[i] & (EXP_TABLE - 1)];
-      t[i] = t[i] - 105553116266496.0;
+      tabv[i] = __shfl_sync(0xffffffffu, tab64, ki[i] & (EXP_TABLE - 1));
+      t[i] = t[i] - 211106232532992.0;
     }
   }
   __device__ __forceinline__ void l12() {
@@ -162,7 +162,10 @@ struct StagedEval {
   }
   __device__ __forceinline__ void l13() {
 #pragma unroll
-    for (int i = 0; i < N; ++i) pl[i] = fma(g[i], 0.0013333558146428443, 0.009618129107628477);
+    for (int i = 0; i < N; ++i) {
+      pl[i] = fma(g[i], 0.00015403530393381608, 0.0013333558146428443);
+      pl[i] = fma(g[i], pl[i], 0.009618129107628477);
+    }
   }
   __device__ __forceinline__ void l14() {
 #pragma unroll
@@ -187,7 +190,7 @@ struct StagedEval {
   __device__ __forceinline__ void l19() {  // apply 2^n, underflow guard, prefactor
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double out = __hiloint2double(__double2hiint(pl[i]) + ((ki[i] >> 6) << 20),
+      const double out = __hiloint2double(__double2hiint(pl[i]) + ((ki[i] >> 5) << 20),
                                           __double2loint(pl[i]));
       val[i] = pref[i] * ((__double2hiint(s[i]) < 0x4085e000) ? out : 0.0);
     }
@@ -215,7 +218,7 @@ struct StagedEval<F, 0> {
   __device__ __forceinline__ void l8() {}
   __device__ __forceinline__ void l9() {}
   __device__ __forceinline__ void l10() {}
-  __device__ __forceinline__ void l11(const double*) {}
+  __device__ __forceinline__ void l11(double) {}
   __device__ __forceinline__ void l12() {}
   __device__ __forceinline__ void l13() {}
   __device__ __forceinline__ void l14() {}
@@ -234,7 +237,7 @@ __device__ __forceinline__ void column_step(double& c0, double& c1, double& v0, 
                                             double& di0, double& di1, bool& ok,
                                             double& prev_pinv, const unsigned* pe, int q, int qb,
                                             double* tiles, const double2* pts2,
-                                            const double* tab64, double noise) {
+                                            double tab64, double noise) {
   constexpr int j = J8, qj = j >> 1, bj = j & 1;
   StagedEval<F, NE> ev;
   const int dep = (__double2hiint(prev_pinv) >> 31) & 1;  // always 0: pins program order
@@ -291,7 +294,7 @@ struct ColCtx {
   const double2* pts2;  // next neighbourhood's (scaled) points
   const double* ys;     // next neighbourhood's targets
   const unsigned* etab;
-  const double* tab64;
+  double tab64;  // this lane's entry of the 2^(j/32) table
   double noise;
   int lane, k;
 };
@@ -320,7 +323,7 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
   double c[T][2];
 #pragma unroll
   for (int I = J; I < T; ++I) {
-    const double2 v = *reinterpret_cast<const double2*>(tiles + tile_base(I, J) + rho * 8 + 2 * q);
+    const double2 v = *reinterpret_cast<const double2*>(tiles + frag_off(I, J, rho, q));
     c[I][0] = v.x;
     c[I][1] = v.y;
   }
@@ -415,16 +418,15 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
 
-  double* tab64 = smem;
-  unsigned* etab = (unsigned*)(tab64 + EXP_TABLE);
-  double* wbase = tab64 + EXP_TABLE + (ROWS + 1) * 16 + (size_t)warp * warp_doubles;
+  const double tab64 = c_exp_tab[lane];
+  unsigned* etab = (unsigned*)smem;
+  double* wbase = smem + (ROWS + 1) * 16 + (size_t)warp * warp_doubles;
   double* tiles = wbase;              // NT*64 image + 2 scratch doubles
   double* pts_buf = tiles + NT * 64 + 2;  // 2 x (k+1) points (x,y); point k = query
   const int pts_doubles = 2 * (KP + 2);
   double* ys_buf = pts_buf + 2 * pts_doubles;  // 2 x k targets
   const int ys_doubles = KP + 2;
 
-  for (int j = threadIdx.x; j < EXP_TABLE; j += blockDim.x) tab64[j] = c_exp_tab[j];
   // dummy entries write -1-ish values to the scratch cell behind the image
   for (int e = threadIdx.x; e < (ROWS + 1) * 32; e += blockDim.x)
     etab[e] = (unsigned)(NT * 64) << 16;
@@ -573,7 +575,7 @@ int launch_fused_pipe(const mgp_problem* p, const Model& model, cudaStream_t str
   constexpr int ROWS = chunk_begin<KP>((KP + 7) / 8);
   const size_t warp_doubles = (size_t)NT * 64 + 2 + 2 * (size_t)(2 * (KP + 2)) + 2 * (size_t)(KP + 2);
   const size_t smem =
-      (EXP_TABLE + (size_t)(ROWS + 1) * 16 + warp_doubles * PIPE_WARPS) * sizeof(double);
+      ((size_t)(ROWS + 1) * 16 + warp_doubles * PIPE_WARPS) * sizeof(double);
   MGP_REQUIRE(smem <= (size_t)max_smem_optin(), MGP_ERR_UNSUPPORTED,
               "pipe kernel shared memory %zu too large", smem);
   long long blocks = (p->b + PIPE_WARPS - 1) / PIPE_WARPS;

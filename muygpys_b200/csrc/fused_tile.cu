@@ -36,28 +36,34 @@ namespace {
 template <int F, int D>
 __device__ __noinline__ void assemble(double* __restrict__ tiles, const double* __restrict__ pts,
                                       const unsigned* __restrict__ etab,
-                                      const double* __restrict__ tab64, int n_elem, int lane,
+                                      double tab64, int n_elem, int lane,
                                       int d, double post_scale, int kernel_id) {
-  int e = lane;
-  for (; e + 32 < n_elem; e += 64) {  // two independent elements in flight
-    const unsigned p0 = etab[e], p1 = etab[e + 32];
-    const double u0 = sqdist<D>(pts, (p0 >> 8) & 255, p0 & 255, d);
-    const double u1 = sqdist<D>(pts, (p1 >> 8) & 255, p1 & 255, d);
-    const double v0 = neg_cov<F>(u0, tab64, post_scale, kernel_id);
-    const double v1 = neg_cov<F>(u1, tab64, post_scale, kernel_id);
-    tiles[p0 >> 16] = v0;
-    tiles[p1 >> 16] = v1;
-  }
-  if (e < n_elem) {
-    const unsigned p0 = etab[e];
-    const double u0 = sqdist<D>(pts, (p0 >> 8) & 255, p0 & 255, d);
-    tiles[p0 >> 16] = neg_cov<F>(u0, tab64, post_scale, kernel_id);
+#ifndef MGP_ASM_WAYS
+#define MGP_ASM_WAYS 2
+#endif
+  constexpr int W = MGP_ASM_WAYS;  // independent elements in flight per lane
+  // uniform trip count (the exp table is read with warp shuffles): lanes past the end
+  // evaluate a dummy entry that lands in the scratch cell behind the image
+  for (int base = 0; base < n_elem; base += 32 * W) {
+    unsigned p[W];
+    double u[W], v[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int e = base + 32 * w + lane;
+      p[w] = etab[e < n_elem ? e : n_elem];
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) u[w] = sqdist<D>(pts, (p[w] >> 8) & 255, p[w] & 255, d);
+#pragma unroll
+    for (int w = 0; w < W; ++w) v[w] = neg_cov<F>(u[w], tab64, post_scale, kernel_id);
+#pragma unroll
+    for (int w = 0; w < W; ++w) tiles[p[w] >> 16] = v[w];
   }
 }
 
 template <int F>
 __device__ __forceinline__ void assemble_d(double* tiles, const double* pts, const unsigned* etab,
-                                           const double* tab64, int n_elem, int lane, int d,
+                                           double tab64, int n_elem, int lane, int d,
                                            double post_scale, int kernel_id) {
   switch (d) {
     case 1: assemble<F, 1>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
@@ -68,7 +74,7 @@ __device__ __forceinline__ void assemble_d(double* tiles, const double* pts, con
 }
 
 __device__ __forceinline__ void assemble_any(int formula, double* tiles, const double* pts,
-                                             const unsigned* etab, const double* tab64,
+                                             const unsigned* etab, double tab64,
                                              int n_elem, int lane, int d, double post_scale,
                                              int kernel_id) {
   switch (formula) {
@@ -96,17 +102,17 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
   const int k = a.k, kp = a.kp, d = a.d, r = a.r;
 
   // CTA-shared: exp table and the table of the flat element list
-  double* tab64 = smem;
-  unsigned* etab = (unsigned*)(tab64 + EXP_TABLE);
-  const int etab_doubles = (((a.n_elem + 1) / 2) + 1) & ~1;
-  double* wbase = tab64 + EXP_TABLE + etab_doubles + (size_t)warp * warp_doubles;
-  double* tiles = wbase;  // NT * 64 doubles, tile-major, row-major inside a tile
+  const double tab64 = c_exp_tab[lane];  // this lane's entry of the 2^(j/32) table
+  unsigned* etab = (unsigned*)smem;       // n_elem entries + 1 dummy
+  const int etab_doubles = (((a.n_elem + 2) / 2) + 1) & ~1;
+  double* wbase = smem + etab_doubles + (size_t)warp * warp_doubles;
+  double* tiles = wbase;  // NT * 64 doubles (+2 scratch), tile-major, see elem_off()
   const int pts_doubles = ((k + 1) * d + 1) & ~1;
   const int ys_doubles = (k * r + 1) & ~1;
-  double* pts_buf = tiles + NT * 64;           // 2 x (k+1) x d coordinates, row k = query
+  double* pts_buf = tiles + NT * 64 + 2;       // 2 x (k+1) x d coordinates, row k = query
   double* ys_buf = pts_buf + 2 * pts_doubles;  // 2 x k x r targets
 
-  for (int j = threadIdx.x; j < EXP_TABLE; j += blockDim.x) tab64[j] = c_exp_tab[j];
+  if (threadIdx.x == 0) etab[a.n_elem] = (unsigned)(NT * 64) << 16;  // dummy -> scratch cell
   for (int e = threadIdx.x; e < a.n_elem; e += blockDim.x) {
     // e < k(k+1)/2: lower triangle in row-major order; then the k cross entries
     const int tri = k * (k + 1) / 2;
@@ -206,6 +212,10 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
       tiles[elem_off(i, i)] -= a.noise_bk ? a.noise_bk[row * k + i] : a.noise;
     __syncwarp();
 
+#ifdef MGP_DEBUG_ASM_ONLY
+    if (lane == 0 && a.var) a.var[row] = tiles[elem_off(kp, 0)];
+    continue;
+#endif
     // ---- left-looking tiled LDL^T in registers ---------------------------------
     // Finished tiles hold U = L D (unscaled columns) in ACCUMULATOR layout (lane
     // (rho,q): columns 2q, 2q+1).  Register 0 of every lane read as an A (or B)
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
 #pragma unroll
       for (int I = J; I < T; ++I) {
         const double2 v =
-            *reinterpret_cast<const double2*>(tiles + tile_base(I, J) + rho * 8 + 2 * q);
+            *reinterpret_cast<const double2*>(tiles + frag_off(I, J, rho, q));
         c[I][0] = v.x;
         c[I][1] = v.y;
       }
@@ -229,13 +239,12 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
       for (int P = 0; P < J; ++P) {
         if (8 * P < kp) {  // tile column P carries eliminated columns
           if (SMEM_L) {
-            const double2 lj = *reinterpret_cast<const double2*>(tiles + tile_base(J, P) +
-                                                                 rho * 8 + 2 * q);
+            const double2 lj = *reinterpret_cast<const double2*>(tiles + frag_off(J, P, rho, q));
             const double b0 = lj.x * dinv0[P], b1 = lj.y * dinv1[P];
 #pragma unroll
             for (int I = J; I < T; ++I) {
-              const double2 li = *reinterpret_cast<const double2*>(tiles + tile_base(I, P) +
-                                                                   rho * 8 + 2 * q);
+              const double2 li =
+                  *reinterpret_cast<const double2*>(tiles + frag_off(I, P, rho, q));
               dmma_acc(c[I][0], c[I][1], li.x, b0);
               dmma_acc(c[I][0], c[I][1], li.y, b1);
             }
@@ -315,7 +324,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
       if (SMEM_L || a.coeffs || 8 * J + 8 > kp) {
 #pragma unroll
         for (int I = J; I < T; ++I)
-          *reinterpret_cast<double2*>(tiles + tile_base(I, J) + rho * 8 + 2 * q) =
+          *reinterpret_cast<double2*>(tiles + frag_off(I, J, rho, q)) =
               make_double2(c[I][0], c[I][1]);
       }
     }
@@ -385,9 +394,9 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
   const int T = tiles_needed(p->k, p->r);
   const int NT = T * (T + 1) / 2;
   // per warp: tile image + double-buffered coordinates and targets (cp.async prefetch)
-  const size_t warp_doubles = (size_t)NT * 64 + 2 * (size_t)((((p->k + 1) * p->d) + 1) & ~1) +
+  const size_t warp_doubles = (size_t)NT * 64 + 2 + 2 * (size_t)((((p->k + 1) * p->d) + 1) & ~1) +
                               2 * (size_t)(((p->k * p->r) + 1) & ~1);
-  const size_t shared_doubles = EXP_TABLE + (size_t)((((a.n_elem + 1) / 2) + 1) & ~1);
+  const size_t shared_doubles = (size_t)((((a.n_elem + 2) / 2) + 1) & ~1);
   const bool smem_l = T > 7;
   int warps = TILE_WARPS;
   while (warps > 1 &&

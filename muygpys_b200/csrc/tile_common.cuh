@@ -8,9 +8,9 @@ namespace {
 
 constexpr int TILE_WARPS = 4;        // warps (neighbourhoods in flight) per CTA
 constexpr int TILE_MAX_D = 8;
-constexpr int EXP_TABLE = 64;
+constexpr int EXP_TABLE = 32;  // 2^(j/32), one entry per lane, looked up with a shuffle
 
-__constant__ double c_exp_tab[EXP_TABLE];  // 2^(j/64), correctly rounded on the host
+__constant__ double c_exp_tab[EXP_TABLE];  // 2^(j/32), correctly rounded on the host
 
 __device__ __forceinline__ double shfl_d(double v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
@@ -49,20 +49,27 @@ __device__ __forceinline__ double sqrt_fast(double x) {
   return (__double2hiint(x) > 0x03c00000) ? s : 0.0;
 }
 
-// exp(-s), s >= 0: 64-entry table of 2^(j/64) + degree-5 polynomial.
-// |abs error| <= ~2.3e-16 (validated against long double on the host).
-__device__ __forceinline__ double exp_neg(double s, const double* __restrict__ tab64) {
-  const double t = fma(s, -1.4426950408889634, 105553116266496.0);
+// exp(-s), s >= 0: 32-entry table of 2^(j/32) + degree-6 polynomial.  The table lives in a
+// REGISTER of each lane (`tabreg` = entry `lane`) and is read with a warp shuffle: the
+// data-dependent shared-memory lookup it replaces cost ~7 bank-conflicted wavefronts per
+// warp and made the assembly phase shared-memory-bound.  Every lane of the warp must call
+// this together.  |abs error| <= ~2.2e-16 (validated against long double on the host).
+__device__ __forceinline__ double exp_neg(double s, double tabreg) {
+  const double LOG2E = 1.4426950408889634;
+  const double MAGIC = 211106232532992.0;  // 1.5 * 2^47: ulp = 2^-5
+  const double t = fma(s, -LOG2E, MAGIC);
   const int ki = __double2loint(t);
-  const double tr = t - 105553116266496.0;
-  const double g = fma(s, -1.4426950408889634, -tr);
-  double p = fma(g, 0.0013333558146428443, 0.009618129107628477);
+  const double tabv = __shfl_sync(0xffffffffu, tabreg, ki & (EXP_TABLE - 1));
+  const double tr = t - MAGIC;
+  const double g = fma(s, -LOG2E, -tr);
+  double p = fma(g, 0.00015403530393381608, 0.0013333558146428443);
+  p = fma(g, p, 0.009618129107628477);
   p = fma(g, p, 0.05550410866482158);
   p = fma(g, p, 0.2402265069591007);
   p = fma(g, p, 0.6931471805599453);
   p = fma(g, p, 1.0);
-  const double res = tab64[ki & (EXP_TABLE - 1)] * p;
-  const int n = ki >> 6;
+  const double res = tabv * p;
+  const int n = ki >> 5;
   const double out = __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
   return (__double2hiint(s) < 0x4085e000) ? out : 0.0;  // s < 700
 }
@@ -101,7 +108,7 @@ enum Formula {
 
 // NEGATED covariance (the tile image holds N = -A)
 template <int F>
-__device__ __forceinline__ double neg_cov(double u2, const double* tab64, double post_scale,
+__device__ __forceinline__ double neg_cov(double u2, double tab64, double post_scale,
                                           int kernel_id) {
   if (F == F_M05) return -exp_neg(sqrt_fast(u2), tab64);
   if (F == F_M15) {
@@ -155,8 +162,16 @@ __device__ __forceinline__ double sqdist(const double* __restrict__ pts, int pi,
 __host__ __device__ __forceinline__ int tile_base(int I, int J) {
   return ((I * (I + 1)) / 2 + J) * 64;
 }
+// Tile image: tile-major, row-major inside a tile, with the rows of odd tile columns swapped
+// pairwise (row ^ 1).  A warp storing 32 consecutive columns of one matrix row then alternates
+// between the two 16-bank windows instead of hitting one of them four times over.
 __device__ __forceinline__ int elem_off(int i, int j) {
-  return tile_base(i >> 3, j >> 3) + (i & 7) * 8 + (j & 7);
+  const int J = j >> 3;
+  return tile_base(i >> 3, J) + ((((i & 7) ^ (J & 1))) << 3) + (j & 7);
+}
+// accumulator-layout fragment (row rho, columns 2q, 2q+1) of tile (I,J)
+__device__ __forceinline__ int frag_off(int I, int J, int rho, int q) {
+  return tile_base(I, J) + ((rho ^ (J & 1)) << 3) + 2 * q;
 }
 
 __device__ __forceinline__ double sel_d(bool p, double a, double b) { return p ? a : b; }
