@@ -328,3 +328,44 @@ def test_high_d_knn_tiled_matches_warp_kernel_and_oracle():
     s1, _ = ops.knn(xd, xd[rows], k + 1)
     assert int(si[0, 0]) == 4000 and int(si[1, 0]) == 17  # the duplicate is the nearest other
     assert torch.equal(s1[2:, 1:], si[2:])
+
+
+SHAPES = [(1, 1, 2), (2, 1, 1), (3, 2, 2), (7, 1, 3), (8, 3, 2), (12, 5, 2), (30, 10, 3),
+          (33, 1, 2), (49, 1, 2), (50, 10, 2), (51, 1, 2), (52, 1, 2), (60, 4, 5), (64, 1, 8),
+          (99, 2, 2), (100, 1, 2), (100, 3, 2), (101, 1, 2), (104, 1, 2), (120, 1, 2)]
+
+
+@pytest.mark.parametrize("k,r,d", SHAPES, ids=lambda v: str(v))
+def test_shape_sweep_tile_vs_generic_vs_oracle(k, r, d):
+    """Every (k, r, d) corner of the tile kernels -- one tile, partial last panel, Schur block
+    spanning two tile rows (r = 10), the register / shared-memory factor split at T = 7/8, the
+    pipelined specialisation at k in 49..52, k beyond the tile kernels -- against the generic
+    kernel and the oracle, for mean, variance, y^T K^-1 y and the fast-mean coefficients."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(1000 * k + 10 * r + d)
+    n, b = 600, 37
+    x = rng.uniform(size=(n, d))
+    y = rng.normal(size=(n, r))
+    q = rng.uniform(size=(b, d))
+    nn, _ = O.knn_exact(x, q, k)
+    kid = int(rng.integers(0, 5))
+    metric = O.METRIC_F2 if kid == O.KERNEL_RBF else O.METRIC_L2
+    ls = 0.3 if metric == O.METRIC_L2 else 0.5
+    kw = dict(kernel_id=kid, metric_id=metric, length_scale=ls, noise=1e-3, scale=1.7,
+              want_yky=True, want_coeffs=True, want_status=True)
+    outs = {}
+    for name, variant in (("auto", 0), ("tile", 2), ("generic", 1)):
+        ops.set_fused_variant(variant)
+        outs[name] = ops.fused_posterior(dev(x), dev(q), None, dev(nn), dev(y), **kw)
+    ops.set_fused_variant(0)
+    Kin, Kcross = O.kernel_tensors(kid, metric, ls, x, q, np.arange(b), nn)
+    pK = O.homoscedastic_perturb(Kin, 1e-3)
+    want = dict(mean=O.posterior_mean(pK, Kcross, y[nn]),
+                var=1.7 * O.diagonal_variance(pK, Kcross),
+                yky=np.einsum("bkr,bkr->b", y[nn], np.linalg.solve(pK, y[nn])),
+                coeffs=np.linalg.solve(pK, y[nn]))
+    for name, out in outs.items():
+        assert int(out["status"].sum()) == 0
+        for key, tol in (("mean", RTOL), ("var", RTOL), ("yky", RTOL), ("coeffs", 1e-9)):
+            assert_close(out[key].cpu().numpy(), want[key], tol, f"{name} {key} k={k} r={r} d={d}")
