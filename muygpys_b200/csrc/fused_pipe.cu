@@ -79,167 +79,80 @@ __device__ __noinline__ void assemble_flat(double* tiles, const double2* pts2,
   if (it < rows) eval_entry<F>(etab[it * 32 + lane], tiles, pts2, tab64, noise);
 }
 
-// The same evaluation cut into dependency LEVELS (N independent entries advance one level per
-// call).  The kernel calls the levels alternately with the levels of the in-tile LDL^T column
-// step, so that program order itself is interleaved: GPUs issue in order within a warp, and
-// ptxas only reorders locally, so this is what lets one stream issue under the other's latency.
-template <int F, int N>
-struct StagedEval {
-  unsigned p[N];
-  double2 a[N], b[N];
-  double dx[N], dy[N], u[N], r[N], g[N], e[N], s[N], pref[N], t[N], tabv[N], pl[N], val[N];
-  int ki[N];
-  __device__ __forceinline__ void l0(const unsigned* pe, int dep, const double2* pts2) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      p[i] = pe[i];
-      a[i] = pts2[((p[i] >> 8) & 255) + dep];
-      b[i] = pts2[p[i] & 255];
-    }
+// One covariance entry cut into 21 dependency LEVELS, grouped in three slices of seven.  The
+// kernel keeps THREE entries in flight, one per slice, and advances each by one slice per
+// in-tile column step, calling the levels of the three slices and of the LDL^T step
+// alternately: GPUs issue in order within a warp and ptxas only reorders locally, so it is the
+// program order itself that must offer four independent instructions per dependency level.
+template <int F>
+struct EvalState {
+  unsigned p;
+  int ki;
+  double u, g, r, e, s, pref, t, tabv, pl;
+  // ---- slice 1: squared distance, start of sqrt ------------------------------------------
+  __device__ __forceinline__ void l0(unsigned entry, int dep, const double2* pts2) {
+    p = entry;
+    const double2 a = pts2[((p >> 8) & 255) + dep], b = pts2[p & 255];
+    g = a.x - b.x;  // dx
+    r = a.y - b.y;  // dy
   }
-  __device__ __forceinline__ void l1() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      dx[i] = a[i].x - b[i].x;
-      dy[i] = a[i].y - b[i].y;
-    }
-  }
-  __device__ __forceinline__ void l2() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) u[i] = dx[i] * dx[i];
-  }
-  __device__ __forceinline__ void l3() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) u[i] = fma(dy[i], dy[i], u[i]);
-  }
-  __device__ __forceinline__ void l4() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) r[i] = rsqrt_seed(u[i]);
-  }
-  __device__ __forceinline__ void l5() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = u[i] * r[i];
-  }
-  __device__ __forceinline__ void l6() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) e[i] = fma(-g[i], r[i], 1.0);
-  }
-  __device__ __forceinline__ void l7() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) r[i] = fma(e[i], 0.375, 0.5);
-  }
+  __device__ __forceinline__ void l1() { u = g * g; }
+  __device__ __forceinline__ void l2() { u = fma(r, r, u); }
+  __device__ __forceinline__ void l3() { r = rsqrt_seed(u); }
+  __device__ __forceinline__ void l4() { g = u * r; }
+  __device__ __forceinline__ void l5() { e = fma(-g, r, 1.0); }
+  __device__ __forceinline__ void l6() { r = fma(e, 0.375, 0.5); }
+  // ---- slice 2: end of sqrt, range reduction of exp(-s), table lookup --------------------
+  __device__ __forceinline__ void l7() { e = e * r; }
   __device__ __forceinline__ void l8() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) e[i] = e[i] * r[i];
+    const double sq = fma(g, e, g);
+    s = (__double2hiint(u) > 0x03c00000) ? sq : 0.0;
   }
-  __device__ __forceinline__ void l9() {  // s = sqrt(u) (0 for u == 0)
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const double sq = fma(g[i], e[i], g[i]);
-      s[i] = (__double2hiint(u[i]) > 0x03c00000) ? sq : 0.0;
-    }
+  __device__ __forceinline__ void l9() {
+    t = fma(s, -1.4426950408889634, 211106232532992.0);
+    if (F == F_M05) pref = -1.0;
+    if (F == F_M15) pref = -1.0 - s;
+    if (F == F_M25) pref = fma(u, -(1.0 / 3.0), -1.0 - s);
   }
-  __device__ __forceinline__ void l10() {  // range reduction of exp(-s); polynomial prefactor
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      t[i] = fma(s[i], -1.4426950408889634, 211106232532992.0);
-      if (F == F_M05) pref[i] = -1.0;
-      if (F == F_M15) pref[i] = -1.0 - s[i];
-      if (F == F_M25) pref[i] = fma(u[i], -(1.0 / 3.0), -1.0 - s[i]);
-    }
+  __device__ __forceinline__ void l10(double tab) {
+    ki = __double2loint(t);
+    tabv = __shfl_sync(0xffffffffu, tab, ki & (EXP_TABLE - 1));
+    t = t - 211106232532992.0;
   }
-  __device__ __forceinline__ void l11(double tab64) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      ki[i] = __double2loint(t[i]);
-      tabv[i] = __shfl_sync(0xffffffffu, tab64, ki[i] & (EXP_TABLE - 1));
-      t[i] = t[i] - 211106232532992.0;
-    }
-  }
-  __device__ __forceinline__ void l12() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = fma(s[i], -1.4426950408889634, -t[i]);
-  }
-  __device__ __forceinline__ void l13() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      pl[i] = fma(g[i], 0.00015403530393381608, 0.0013333558146428443);
-      pl[i] = fma(g[i], pl[i], 0.009618129107628477);
-    }
-  }
-  __device__ __forceinline__ void l14() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) pl[i] = fma(g[i], pl[i], 0.05550410866482158);
-  }
-  __device__ __forceinline__ void l15() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) pl[i] = fma(g[i], pl[i], 0.2402265069591007);
-  }
-  __device__ __forceinline__ void l16() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) pl[i] = fma(g[i], pl[i], 0.6931471805599453);
-  }
-  __device__ __forceinline__ void l17() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) pl[i] = fma(g[i], pl[i], 1.0);
-  }
-  __device__ __forceinline__ void l18() {
-#pragma unroll
-    for (int i = 0; i < N; ++i) pl[i] = tabv[i] * pl[i];
-  }
-  __device__ __forceinline__ void l19() {  // apply 2^n, underflow guard, prefactor
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const double out = __hiloint2double(__double2hiint(pl[i]) + ((ki[i] >> 5) << 20),
-                                          __double2loint(pl[i]));
-      val[i] = pref[i] * ((__double2hiint(s[i]) < 0x4085e000) ? out : 0.0);
-    }
+  __device__ __forceinline__ void l11() { g = fma(s, -1.4426950408889634, -t); }
+  __device__ __forceinline__ void l12() { pl = fma(g, 0.00015403530393381608, 0.0013333558146428443); }
+  __device__ __forceinline__ void l13() { pl = fma(g, pl, 0.009618129107628477); }
+  // ---- slice 3: rest of the polynomial, scaling, store ------------------------------------
+  __device__ __forceinline__ void l14() { pl = fma(g, pl, 0.05550410866482158); }
+  __device__ __forceinline__ void l15() { pl = fma(g, pl, 0.2402265069591007); }
+  __device__ __forceinline__ void l16() { pl = fma(g, pl, 0.6931471805599453); }
+  __device__ __forceinline__ void l17() { pl = fma(g, pl, 1.0); }
+  __device__ __forceinline__ void l18() { pl = tabv * pl; }
+  __device__ __forceinline__ void l19() {
+    const double out = __hiloint2double(__double2hiint(pl) + ((ki >> 5) << 20), __double2loint(pl));
+    pl = pref * ((__double2hiint(s) < 0x4085e000) ? out : 0.0);
   }
   __device__ __forceinline__ void l20(double* tiles, double noise) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const bool diag = ((p[i] >> 8) & 255) == (p[i] & 255);
-      tiles[p[i] >> 16] = val[i] - (diag ? noise : 0.0);
-    }
+    const bool diag = ((p >> 8) & 255) == (p & 255);
+    tiles[p >> 16] = pl - (diag ? noise : 0.0);
   }
 };
 
-// N == 0: nothing to evaluate in this step
-template <int F>
-struct StagedEval<F, 0> {
-  __device__ __forceinline__ void l0(const unsigned*, int, const double2*) {}
-  __device__ __forceinline__ void l1() {}
-  __device__ __forceinline__ void l2() {}
-  __device__ __forceinline__ void l3() {}
-  __device__ __forceinline__ void l4() {}
-  __device__ __forceinline__ void l5() {}
-  __device__ __forceinline__ void l6() {}
-  __device__ __forceinline__ void l7() {}
-  __device__ __forceinline__ void l8() {}
-  __device__ __forceinline__ void l9() {}
-  __device__ __forceinline__ void l10() {}
-  __device__ __forceinline__ void l11(double) {}
-  __device__ __forceinline__ void l12() {}
-  __device__ __forceinline__ void l13() {}
-  __device__ __forceinline__ void l14() {}
-  __device__ __forceinline__ void l15() {}
-  __device__ __forceinline__ void l16() {}
-  __device__ __forceinline__ void l17() {}
-  __device__ __forceinline__ void l18() {}
-  __device__ __forceinline__ void l19() {}
-  __device__ __forceinline__ void l20(double*, double) {}
-};
-
-// One in-tile LDL^T column step of the diagonal tile (cJ) and the identity tile (v), with the
-// levels of NE element evaluations of the next neighbourhood woven between its levels.
-template <int F, int NE, int J8>
+// In-tile LDL^T column step S (global index over the whole factorisation) of the diagonal
+// tile (c0,c1) and the identity tile (v0,v1).  Entry S of the next neighbourhood starts its
+// first slice here, entry S-1 runs its second and entry S-2 its third.
+template <int F, int S, int NEV>
 __device__ __forceinline__ void column_step(double& c0, double& c1, double& v0, double& v1,
                                             double& di0, double& di1, bool& ok,
-                                            double& prev_pinv, const unsigned* pe, int q, int qb,
-                                            double* tiles, const double2* pts2,
-                                            double tab64, double noise) {
-  constexpr int j = J8, qj = j >> 1, bj = j & 1;
-  StagedEval<F, NE> ev;
+                                            double& prev_pinv, EvalState<F> (&ev)[3],
+                                            const unsigned* etab, int lane, int q, int qb,
+                                            double* tiles, const double2* pts2, double tab64,
+                                            double noise) {
+  constexpr int j = S & 7, qj = j >> 1, bj = j & 1;
+  constexpr bool HAS_A = S < NEV, HAS_B = S >= 1 && S - 1 < NEV, HAS_C = S >= 2 && S - 2 < NEV;
+  EvalState<F>& A = ev[S % 3];
+  EvalState<F>& B = ev[(S + 2) % 3];
+  EvalState<F>& C = ev[(S + 1) % 3];
   const int dep = (__double2hiint(prev_pinv) >> 31) & 1;  // always 0: pins program order
   const double cj = bj == 0 ? c0 : c1;
   // level 0: the five shuffles of this step read the (final, unscaled) column j
@@ -248,24 +161,39 @@ __device__ __forceinline__ void column_step(double& c0, double& c1, double& v0, 
   const double uc1 = shfl_d(cj, (2 * q + 1) * 4 + qj);
   const double lr = shfl_d(cj, qb | qj);
   const double vr = shfl_d(bj == 0 ? v0 : v1, qb | qj);
-  ev.l0(pe, dep, pts2);
-  ev.l1();
-  ev.l2();
+  if (HAS_A) A.l0(etab[S * 32 + lane + dep], 0, pts2);
+  if (HAS_B) B.l7();
+  if (HAS_C) C.l14();
+  // level 1
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
   ok = ok && (p > 0.0);
-  ev.l3();
-  ev.l4();
+  if (HAS_A) A.l1();
+  if (HAS_B) B.l8();
+  if (HAS_C) C.l15();
+  // level 2
   const double e = fma(-p, r, 1.0);
-  ev.l5();
+  if (HAS_A) A.l2();
+  if (HAS_B) B.l9();
+  if (HAS_C) C.l16();
+  // level 3
   const double q1 = r * e, w = 1.0 + e;
-  ev.l6();
+  if (HAS_A) A.l3();
+  if (HAS_B) B.l10(tab64);
+  if (HAS_C) C.l17();
+  // level 4
   const double pinv = fma(q1, w, r);
-  ev.l7();
+  if (HAS_A) A.l4();
+  if (HAS_B) B.l11();
+  if (HAS_C) C.l18();
+  // level 5
   if (bj == 0) di0 = sel_d(q == qj, pinv, di0); else di1 = sel_d(q == qj, pinv, di1);
   const double t0 = sel_d(2 * q > j, uc0, 0.0) * pinv;
   const double t1 = sel_d(2 * q + 1 > j, uc1, 0.0) * pinv;
-  ev.l8();
+  if (HAS_A) A.l5();
+  if (HAS_B) B.l12();
+  if (HAS_C) C.l19();
+  // level 6
   if (j < 6) {
     c0 = fma(-lr, t0, c0);
     v0 = fma(-vr, t0, v0);
@@ -274,18 +202,9 @@ __device__ __forceinline__ void column_step(double& c0, double& c1, double& v0, 
     c1 = fma(-lr, t1, c1);
     v1 = fma(-vr, t1, v1);
   }
-  ev.l9();
-  ev.l10();
-  ev.l11(tab64);
-  ev.l12();
-  ev.l13();
-  ev.l14();
-  ev.l15();
-  ev.l16();
-  ev.l17();
-  ev.l18();
-  ev.l19();
-  ev.l20(tiles, noise);
+  if (HAS_A) A.l6();
+  if (HAS_B) B.l13();
+  if (HAS_C) C.l20(tiles, noise);
   prev_pinv = pinv;
 }
 
@@ -305,7 +224,8 @@ template <int T, int KP, int F, int J>
 __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][T],
                                                double (&l1)[T][T], double (&dinv0)[T],
                                                double (&dinv1)[T], bool& ok, double& prev_pinv,
-                                               double& c_last0, double& c_last1) {
+                                               EvalState<F> (&ev)[3], double& c_last0,
+                                               double& c_last1) {
   constexpr int JE = (KP + 7) / 8;
   constexpr int ZF = (KP - 3) >> 3;
 #ifdef MGP_DEBUG_SKIP_EVAL
@@ -313,10 +233,14 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
 #else
   constexpr int CI_ = (J < JE) ? chunk_iters<KP>(J) : 0;
 #endif
-  constexpr int CB_ = chunk_begin<KP>(J < JE ? J : 0);
+  (void)CI_;
+  constexpr int NEV = chunk_begin<KP>(JE);  // element evaluations (table rows) per neighbourhood
   constexpr int NC_ = (KP - 8 * J) >= 8 ? 8 : ((KP - 8 * J) > 0 ? (KP - 8 * J) : 1);
   constexpr int ncols = (J < JE) ? NC_ : 0;
-  static_assert(CI_ <= 2 * NC_, "at most two evaluations per column step");
+  // entry S starts at column step S: it must belong to a tile column that has been handed
+  // over already (chunk_begin(J) >= 8 J for every J) and finish before the last step
+  static_assert(chunk_begin<KP>(J < JE ? J : 0) >= 8 * (J < JE ? J : 0), "entry starts too early");
+  static_assert(NEV + 2 <= KP, "the last entries must drain before the factorisation ends");
   const int lane = x.lane, rho = lane >> 2, q = lane & 3, qb = lane & ~3;
   double* tiles = x.tiles;
   // ---- current neighbourhood: pick up tile column J, then hand its cells over ----------
@@ -327,9 +251,6 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
     c[I][0] = v.x;
     c[I][1] = v.y;
   }
-  unsigned pe[CI_ > 0 ? CI_ : 1];  // this column's table entries, fetched in one batch
-#pragma unroll
-  for (int it = 0; it < CI_; ++it) pe[it] = x.etab[(CB_ + it) * 32 + lane];
   __syncwarp();
 #pragma unroll
   for (int I = (ZF > J ? ZF : J); I < T; ++I)
@@ -370,11 +291,9 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
     double v0 = (rho == 2 * q) ? 1.0 : 0.0, v1 = (rho == 2 * q + 1) ? 1.0 : 0.0;
     double di0 = 0.0, di1 = 0.0;
 #define MGP_STEP(JJ)                                                                          \
-  if (JJ < ncols) {                                                                           \
-    constexpr int lo_ = (CI_ * JJ) / NC_, hi_ = (CI_ * (JJ + 1)) / NC_;                       \
-    column_step<F, hi_ - lo_, JJ>(c[J][0], c[J][1], v0, v1, di0, di1, ok, prev_pinv, pe + lo_, \
-                                  q, qb, tiles, x.pts2, x.tab64, x.noise);                    \
-  }
+  if (JJ < ncols)                                                                             \
+    column_step<F, 8 * J + JJ, NEV>(c[J][0], c[J][1], v0, v1, di0, di1, ok, prev_pinv, ev,    \
+                                    x.etab, lane, q, qb, tiles, x.pts2, x.tab64, x.noise);
     MGP_STEP(0) MGP_STEP(1) MGP_STEP(2) MGP_STEP(3)
     MGP_STEP(4) MGP_STEP(5) MGP_STEP(6) MGP_STEP(7)
 #undef MGP_STEP
@@ -400,7 +319,8 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
     c_last0 = c[T - 1][0];
     c_last1 = c[T - 1][1];
   } else {
-    process_column<T, KP, F, J + 1>(x, l0, l1, dinv0, dinv1, ok, prev_pinv, c_last0, c_last1);
+    process_column<T, KP, F, J + 1>(x, l0, l1, dinv0, dinv1, ok, prev_pinv, ev, c_last0,
+                                    c_last1);
   }
 }
 
@@ -431,20 +351,39 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
   for (int e = threadIdx.x; e < (ROWS + 1) * 32; e += blockDim.x)
     etab[e] = (unsigned)(NT * 64) << 16;
   __syncthreads();
-  for (int j = warp; j < k; j += PIPE_WARPS) {
-    // matrix column j: rows j..k-1 of K, then the cross-covariance (tile row KP, point k)
-    const int J = j >> 3;
-    int base = 0;
-    for (int jj = 8 * J; jj < j; ++jj) base += k - jj + 1;
-    for (int o = lane; o <= k - j; o += 32) {
-      const int pi = (o == k - j) ? k : j + o;
-      const int ti = (o == k - j) ? KP : j + o;
-      int cb = 0;  // first table row of tile column J's chunk
+  // Tile column J's chunk lists its cells ROW-major: rows 8J..k-1 of K (columns 8J..min(8J+7,
+  // row)), then the cross-covariance row (tile row KP, point k).  A warp then stores runs of up
+  // to 8 consecutive columns of consecutive rows (2-way bank conflicts instead of the 16-way a
+  // column-major order gives) and its point loads are multicasts of <= 4 + 8 addresses.
+  for (int J = warp; J < JE; J += PIPE_WARPS) {
+    int cb = 0;  // first table row of this chunk
 #pragma unroll
-      for (int c = 0; c < JE; ++c)
-        if (c < J) cb += chunk_iters<KP>(c);
-      etab[cb * 32 + base + o] =
-          ((unsigned)elem_off(ti, j) << 16) | ((unsigned)pi << 8) | (unsigned)j;
+    for (int c = 0; c < JE; ++c)
+      if (c < J) cb += chunk_iters<KP>(c);
+    const int c0 = 8 * J, ncol = min(8, k - c0);
+    if (ncol <= 0) continue;
+    // rows c0 .. c0+ncol-1 form a triangle (row i has i-c0+1 cells), later rows have ncol cells
+    const int tri = ncol * (ncol + 1) / 2;
+    const int full_rows = k - (c0 + ncol);            // K rows below the triangle
+    const int total = tri + (full_rows + 1) * ncol;   // + the cross-covariance row
+    for (int e = lane; e < total; e += 32) {
+      int ti, pi, j;
+      if (e < tri) {
+        int rr = 0;
+        while ((rr + 1) * (rr + 2) / 2 <= e) ++rr;
+        ti = pi = c0 + rr;
+        j = c0 + e - rr * (rr + 1) / 2;
+      } else {
+        const int f = e - tri, rr = f / ncol;
+        j = c0 + f - rr * ncol;
+        if (rr < full_rows) {
+          ti = pi = c0 + ncol + rr;
+        } else {
+          ti = KP;
+          pi = k;
+        }
+      }
+      etab[cb * 32 + e] = ((unsigned)elem_off(ti, j) << 16) | ((unsigned)pi << 8) | (unsigned)j;
     }
   }
   __syncthreads();
@@ -539,7 +478,8 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
     ctx.noise = noise;
     ctx.lane = lane;
     ctx.k = k;
-    process_column<T, KP, F, 0>(ctx, l0, l1, dinv0, dinv1, ok, prev_pinv, c_last0, c_last1);
+    EvalState<F> ev[3];
+    process_column<T, KP, F, 0>(ctx, l0, l1, dinv0, dinv1, ok, prev_pinv, ev, c_last0, c_last1);
     {
       // Schur complement straight from the accumulator registers of the last tile
       const double cv = (LI & 1) ? c_last1 : c_last0;
