@@ -179,7 +179,7 @@ class MuyGPS:
             scale=self.scale() if scale is None else scale, **want)
 
     def _fused_pipelined(self, indices, nn_indices, test_features, train_features,
-                         train_targets, want_mean, want_var, chunks: int = 4):
+                         train_targets, want_mean, want_var, chunks: int = 8):
         """Host-resident index/feature batches: upload chunk i+1 on a side stream while
         chunk i is in the fused kernel, so the end-to-end rate is max(PCIe, compute)."""
         x, y = fdev(train_features), fdev(train_targets)
