@@ -24,6 +24,10 @@
 //
 // Supported shapes: roundup8(roundup4(k) + 1 + r) <= 56 (one warp's registers),
 // d <= 8.  Everything else takes the generic shared-memory kernel.
+#include <cstdint>
+#include <cstdlib>
+
+#include "gram.cuh"
 #include "tile_common.cuh"
 
 namespace mgp {
@@ -53,7 +57,9 @@ __device__ __noinline__ void assemble(double* __restrict__ tiles, const double* 
       p[w] = etab[e < n_elem ? e : n_elem];
     }
 #pragma unroll
-    for (int w = 0; w < W; ++w) u[w] = sqdist<D>(pts, (p[w] >> 8) & 255, p[w] & 255, d);
+    for (int w = 0; w < W; ++w)
+      u[w] = (D < 0) ? tiles[p[w] >> 16]  // gram mode: the raw distance is already in place
+                     : sqdist<(D < 0 ? 0 : D)>(pts, (p[w] >> 8) & 255, p[w] & 255, d);
 #pragma unroll
     for (int w = 0; w < W; ++w) v[w] = neg_cov<F>(u[w], tab64, post_scale, kernel_id);
 #pragma unroll
@@ -69,6 +75,7 @@ __device__ __forceinline__ void assemble_d(double* tiles, const double* pts, con
     case 1: assemble<F, 1>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
     case 2: assemble<F, 2>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
     case 3: assemble<F, 3>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
+    case -1: assemble<F, -1>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id); break;
     default: assemble<F, 0>(tiles, pts, etab, tab64, n_elem, lane, d, post_scale, kernel_id);
   }
 }
@@ -92,7 +99,7 @@ __device__ __forceinline__ void assemble_any(int formula, double* tiles, const d
 // SMEM_L = true : finished tiles are written back over their own cells of the shared-memory
 //                 image and re-read as DMMA fragments (one LDS.128 per tile per use), which
 //                 takes T up to 13 (k ~ 100, BASELINE config C4) at one CTA per SM.
-template <int T, bool SMEM_L>
+template <int T, bool SMEM_L, bool GRAM>
 __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
     fused_tile_kernel(const TileArgs a, size_t warp_doubles) {
   extern __shared__ double smem[];
@@ -105,14 +112,17 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
   const double tab64 = c_exp_tab[lane];  // this lane's entry of the 2^(j/32) table
   unsigned* etab = (unsigned*)smem;       // n_elem entries + 1 dummy
   const int etab_doubles = (((a.n_elem + 2) / 2) + 1) & ~1;
-  double* wbase = smem + etab_doubles + (size_t)warp * warp_doubles;
+  double* sscale = smem + etab_doubles;  // gram mode: per-feature multipliers (anisotropic)
+  double* wbase = sscale + MGP_MAX_ANISO_DIM + (size_t)warp * warp_doubles;
   double* tiles = wbase;  // NT * 64 doubles (+2 scratch), tile-major, see elem_off()
-  const int pts_doubles = ((k + 1) * d + 1) & ~1;
+  const int ds = GRAM ? 0 : d;  // staged coordinates per point
+  const int pts_doubles = ((k + 1) * ds + 1) & ~1;
   const int ys_doubles = (k * r + 1) & ~1;
   double* pts_buf = tiles + NT * 64 + 2;       // 2 x (k+1) x d coordinates, row k = query
   double* ys_buf = pts_buf + 2 * pts_doubles;  // 2 x k x r targets
 
   if (threadIdx.x == 0) etab[a.n_elem] = (unsigned)(NT * 64) << 16;  // dummy -> scratch cell
+  if (GRAM && threadIdx.x < MGP_MAX_ANISO_DIM) sscale[threadIdx.x] = a.coord_scale[threadIdx.x];
   for (int e = threadIdx.x; e < a.n_elem; e += blockDim.x) {
     // e < k(k+1)/2: lower triangle in row-major order; then the k cross entries
     const int tri = k * (k + 1) / 2;
@@ -149,8 +159,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
   auto issue_rows = [&](int buf, int i, long long src) {
     if (src < 0) return;
     const double* px = ((i == k) ? a.query_x : a.train_x) + src * d;
-    double* dst = pts_buf + buf * pts_doubles + i * d;
-    for (int f = 0; f < d; ++f) cp_async8(dst + f, px + f);
+    double* dst = pts_buf + buf * pts_doubles + i * ds;
+    for (int f = 0; f < ds; ++f) cp_async8(dst + f, px + f);
     if (i < k && a.train_y) {
       const double* py = a.train_y + src * r;
       double* dy = ys_buf + buf * ys_doubles + i * r;
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
     double* pts = pts_buf + buf * pts_doubles;
     const double* ys = ys_buf + buf * ys_doubles;
     // fold the length scale(s) into the staged coordinates; scatter -y into rows kp+1+c
-    for (int e = lane; e < (k + 1) * d; e += 32) pts[e] *= a.coord_scale[e % d];
+    for (int e = lane; e < (k + 1) * ds; e += 32) pts[e] *= a.coord_scale[GRAM ? 0 : e % ds];
     if (a.train_y)
       for (int e = lane; e < k * r; e += 32) {
         const int i = e / r, c = e - i * r;
@@ -205,8 +215,29 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
     __syncwarp();
 
     // ---- covariance assembly -------------------------------------------------
-    assemble_any(a.formula, tiles, pts, etab, tab64, a.n_elem, lane, d, a.post_scale,
-                 a.kernel_id);
+    if (GRAM) {
+      GramCtx g;
+      g.train_x = a.train_x;
+      g.qrow = a.query_x + (a.query_idx ? a.query_idx[row] : row) * d;
+      g.nn_row = a.nn_idx + row * k;
+      g.scale = a.aniso ? sscale : nullptr;
+      g.cs2 = a.aniso ? 1.0 : a.coord_scale[0] * a.coord_scale[0];
+      g.k = k;
+      g.kp = kp;
+      g.d = d;
+      if (a.gram == 2) {
+        if (a.aniso) gram_distances<true, true>(tiles, g, lane);
+        else gram_distances<true, false>(tiles, g, lane);
+      } else {
+        if (a.aniso) gram_distances<false, true>(tiles, g, lane);
+        else gram_distances<false, false>(tiles, g, lane);
+      }
+      __syncwarp();
+      gram_fixup(tiles, etab, g, lane);
+      __syncwarp();
+    }
+    assemble_any(a.formula, tiles, pts, etab, tab64, a.n_elem, lane, GRAM ? -1 : d,
+                 a.post_scale, a.kernel_id);
     __syncwarp();
     for (int i = lane; i < k; i += 32)  // nugget on the diagonal (N = -(K + eps))
       tiles[elem_off(i, i)] -= a.noise_bk ? a.noise_bk[row * k + i] : a.noise;
@@ -372,6 +403,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
 
 }  // namespace
 
+static const int g_gram_off = getenv("MGP_NO_GRAM") != nullptr;  // dev switch: generic kernel for d > 8
 static int g_variant = 0;  // 0 auto (pipe > tile > generic), 1 generic, 2 tile, 3 pipe
 
 int fused_variant() { return g_variant; }
@@ -379,7 +411,7 @@ int fused_variant() { return g_variant; }
 int fused_tile_supported(const mgp_problem* p, const Model& model) {
   (void)model;
   if (g_variant == 1) return 0;
-  if (p->d > TILE_MAX_D) return 0;
+  if (p->d > TILE_MAX_D && g_gram_off) return 0;
   if (p->k > 127) return 0;  // the row prefetch stages at most 128 points per warp
   return tiles_needed(p->k, p->r) <= 13;
 }
@@ -394,9 +426,15 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
   const int T = tiles_needed(p->k, p->r);
   const int NT = T * (T + 1) / 2;
   // per warp: tile image + double-buffered coordinates and targets (cp.async prefetch)
-  const size_t warp_doubles = (size_t)NT * 64 + 2 + 2 * (size_t)((((p->k + 1) * p->d) + 1) & ~1) +
+  const int ds = a.gram ? 0 : p->d;
+  const size_t warp_doubles = (size_t)NT * 64 + 2 + 2 * (size_t)((((p->k + 1) * ds) + 1) & ~1) +
                               2 * (size_t)(((p->k * p->r) + 1) & ~1);
-  const size_t shared_doubles = (size_t)((((a.n_elem + 2) / 2) + 1) & ~1);
+  const size_t shared_doubles =
+      (size_t)((((a.n_elem + 2) / 2) + 1) & ~1) + MGP_MAX_ANISO_DIM;
+  // one LDG.128 per lane per row needs even d and 16-byte aligned arrays
+  if (a.gram && p->d % 2 == 0 && ((uintptr_t)p->train_x % 16 == 0) &&
+      ((uintptr_t)p->query_x % 16 == 0))
+    a.gram = 2;
   const bool smem_l = T > 7;
   int warps = TILE_WARPS;
   while (warps > 1 &&
@@ -410,9 +448,17 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
   if (blocks > cap) blocks = cap;
 #define MGP_TILE(TT, SL)                                                                      \
   case TT:                                                                                    \
-    cudaFuncSetAttribute(fused_tile_kernel<TT, SL>,                                           \
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-    fused_tile_kernel<TT, SL><<<(unsigned)blocks, warps * 32, smem, stream>>>(a, warp_doubles); \
+    if (a.gram) {                                                                             \
+      cudaFuncSetAttribute(fused_tile_kernel<TT, SL, true>,                                   \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+      fused_tile_kernel<TT, SL, true><<<(unsigned)blocks, warps * 32, smem, stream>>>(        \
+          a, warp_doubles);                                                                   \
+    } else {                                                                                  \
+      cudaFuncSetAttribute(fused_tile_kernel<TT, SL, false>,                                  \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+      fused_tile_kernel<TT, SL, false><<<(unsigned)blocks, warps * 32, smem, stream>>>(       \
+          a, warp_doubles);                                                                   \
+    }                                                                                         \
     break;
   switch (T) {
     MGP_TILE(1, false)

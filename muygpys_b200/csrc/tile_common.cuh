@@ -91,7 +91,9 @@ struct TileArgs {
   int n_elem;      // k(k+1)/2 + k table entries
   double noise, scale;
   int formula;     // Formula below
-  double coord_scale[TILE_MAX_D];  // per-feature multiplier folded into staged coordinates
+  double coord_scale[MGP_MAX_ANISO_DIM];  // per-feature multiplier folded into the coordinates
+  int gram;        // d > TILE_MAX_D: distances from DMMA Gram tiles (gram.cuh), rows not staged
+  int aniso;       // coord_scale differs per feature
   double post_scale;               // F2 metric with Matern: s = post_scale * u2
   int kernel_id;
 };
@@ -249,8 +251,10 @@ static inline int fill_tile_args(const mgp_problem* p, const Model& model, TileA
   if (model.kernel_id == MGP_KERNEL_MATERN_15) kconst = 1.7320508075688772;
   if (model.kernel_id == MGP_KERNEL_MATERN_25) kconst = 2.23606797749979;
   a.post_scale = 1.0;
-  for (int f = 0; f < TILE_MAX_D; ++f) a.coord_scale[f] = 1.0;
-  for (int f = 0; f < p->d; ++f) {
+  a.gram = p->d > TILE_MAX_D;
+  a.aniso = model.aniso;
+  for (int f = 0; f < MGP_MAX_ANISO_DIM; ++f) a.coord_scale[f] = 1.0;
+  for (int f = 0; f < p->d && f < MGP_MAX_ANISO_DIM; ++f) {
     double inv = model.aniso ? model.inv_ls_vec[f]
                              : (model.metric_id == MGP_METRIC_L2 ? model.inv_ls
                                                                   : sqrt(model.inv_ls));

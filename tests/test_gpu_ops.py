@@ -369,3 +369,78 @@ def test_shape_sweep_tile_vs_generic_vs_oracle(k, r, d):
         assert int(out["status"].sum()) == 0
         for key, tol in (("mean", RTOL), ("var", RTOL), ("yky", RTOL), ("coeffs", 1e-9)):
             assert_close(out[key].cpu().numpy(), want[key], tol, f"{name} {key} k={k} r={r} d={d}")
+
+
+HIGH_D_SHAPES = [(30, 10, 784, False), (5, 1, 9, False), (30, 1, 10, True), (50, 1, 16, False),
+                 (63, 2, 33, False), (64, 1, 12, True), (100, 1, 20, False), (31, 3, 11, True),
+                 (8, 2, 100, False), (40, 1, 32, True)]
+
+
+@pytest.mark.parametrize("k,r,d,aniso", HIGH_D_SHAPES, ids=lambda v: str(v))
+def test_high_dimensional_gram_assembly(k, r, d, aniso):
+    """d > 8: the tile kernel takes its squared distances from query-centred DMMA Gram tiles
+    (csrc/gram.cuh) -- even / odd d (vector / scalar row loads), anisotropic scaling, one to four
+    row blocks (k = 100 exercises the off-diagonal blocks) -- against the generic kernel and the
+    oracle."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(77 * k + 3 * r + d)
+    n, b = 500, 41
+    x = rng.uniform(size=(n, d)) + 5.0          # far from the origin: centring must matter
+    y = rng.normal(size=(n, r))
+    q = rng.uniform(size=(b, d)) + 5.0
+    nn, _ = O.knn_exact(x, q, k)
+    kid = int(rng.integers(0, 5))
+    metric = O.METRIC_F2 if kid == O.KERNEL_RBF else O.METRIC_L2
+    base = (0.5 if metric == O.METRIC_L2 else 0.7) * np.sqrt(d)
+    ls = base * rng.uniform(0.7, 1.4, size=d) if aniso else base
+    kw = dict(kernel_id=kid, metric_id=metric, length_scale=ls, noise=1e-3, scale=0.9,
+              want_yky=True, want_coeffs=True, want_status=True)
+    outs = {}
+    for name, variant in (("auto", 0), ("generic", 1)):
+        ops.set_fused_variant(variant)
+        outs[name] = ops.fused_posterior(dev(x), dev(q), None, dev(nn), dev(y), **kw)
+    ops.set_fused_variant(0)
+    Kin, Kcross = O.kernel_tensors(kid, metric, ls, x, q, np.arange(b), nn)
+    pK = O.homoscedastic_perturb(Kin, 1e-3)
+    want = dict(mean=O.posterior_mean(pK, Kcross, y[nn]),
+                var=0.9 * O.diagonal_variance(pK, Kcross),
+                yky=np.einsum("bkr,bkr->b", y[nn], np.linalg.solve(pK, y[nn])),
+                coeffs=np.linalg.solve(pK, y[nn]))
+    for name, out in outs.items():
+        assert int(out["status"].sum()) == 0
+        for key, tol in (("mean", RTOL), ("var", RTOL), ("yky", RTOL), ("coeffs", 1e-9)):
+            assert_close(out[key].cpu().numpy(), want[key], tol, f"{name} {key} k={k} r={r} d={d}")
+
+
+@pytest.mark.parametrize("kid", [O.KERNEL_MATERN_05, O.KERNEL_MATERN_25, O.KERNEL_RBF])
+def test_high_dimensional_gram_cancellation_fixup(kid):
+    """Gram-identity distances cancel when two neighbours are much closer to each other than to
+    the query: exact duplicates, near-duplicates (1e-7 apart) and queries far outside their
+    neighbourhood must still match the oracle's direct differences (Matern 1/2 is not smooth at
+    0, so a distance error of 1e-14 would show up as 1e-7 in the covariance)."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(4242 + kid)
+    n, b, k, d, r = 300, 23, 20, 24, 2
+    x = rng.normal(size=(n, d))
+    x[1] = x[0]                                   # exact duplicate
+    x[3] = x[2] + 1e-7 * rng.normal(size=d)       # near duplicate
+    x[5] = x[4] + 1e-3 * rng.normal(size=d)
+    y = rng.normal(size=(n, r))
+    q = rng.normal(size=(b, d))
+    q[:8] = x[[0, 2, 4, 0, 2, 4, 0, 2]] + 0.05 * rng.normal(size=(8, d))  # near the duplicates
+    q[8:12] += 40.0                               # far outside the data: everything cancels
+    nn, _ = O.knn_exact(x, q, k)
+    metric = O.METRIC_F2 if kid == O.KERNEL_RBF else O.METRIC_L2
+    ls = 3.0 if metric == O.METRIC_L2 else 4.0
+    noise = 1e-2
+    ops.set_fused_variant(0)
+    out = ops.fused_posterior(dev(x), dev(q), None, dev(nn), dev(y), kernel_id=kid,
+                              metric_id=metric, length_scale=ls, noise=noise, want_status=True)
+    Kin, Kcross = O.kernel_tensors(kid, metric, ls, x, q, np.arange(b), nn)
+    pK = O.homoscedastic_perturb(Kin, noise)
+    assert int(out["status"].sum()) == 0
+    # rows 8..11 have Kcross ~ 0; compare them on the absolute scale of the others
+    assert_close(out["mean"].cpu().numpy(), O.posterior_mean(pK, Kcross, y[nn]), 1e-9, "mean")
+    assert_close(out["var"].cpu().numpy(), O.diagonal_variance(pK, Kcross), 1e-9, "var")
