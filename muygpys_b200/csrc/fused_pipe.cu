@@ -269,11 +269,12 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
   for (int P = 0; P < J; ++P) {
     if (P < JE) {
       const double b0 = l0[J][P] * dinv0[P], b1 = l1[J][P] * dinv1[P];
+      // even slices of every tile first, then the odd ones: back-to-back DMMAs on the same
+      // accumulator would serialise on the DMMA latency
 #pragma unroll
-      for (int I = J; I < T; ++I) {
-        dmma_acc(c[I][0], c[I][1], l0[I][P], b0);
-        dmma_acc(c[I][0], c[I][1], l1[I][P], b1);
-      }
+      for (int I = J; I < T; ++I) dmma_acc(c[I][0], c[I][1], l0[I][P], b0);
+#pragma unroll
+      for (int I = J; I < T; ++I) dmma_acc(c[I][0], c[I][1], l1[I][P], b1);
     }
   }
 #pragma unroll
@@ -307,12 +308,12 @@ __device__ __forceinline__ void process_column(const ColCtx& x, double (&l0)[T][
       const double bm0 = sel_d(par, e1, e0), bm1 = sel_d(par, o1, o0);
 #pragma unroll
       for (int I = J + 1; I < T; ++I) {
-        double n0 = 0.0, n1 = 0.0;
-        dmma_acc(n0, n1, c[I][0], bm0);
-        dmma_acc(n0, n1, c[I][1], bm1);
-        l0[I][J] = n0;
-        l1[I][J] = n1;
+        l0[I][J] = 0.0;
+        l1[I][J] = 0.0;
+        dmma_acc(l0[I][J], l1[I][J], c[I][0], bm0);
       }
+#pragma unroll
+      for (int I = J + 1; I < T; ++I) dmma_acc(l0[I][J], l1[I][J], c[I][1], bm1);
     }
   }
   if constexpr (J == T - 1) {

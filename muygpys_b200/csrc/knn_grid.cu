@@ -11,8 +11,9 @@
 // both kernels return bit-identical indices and squared distances
 // (NN_Wrapper._get_nns semantics, S/neighbors.py:213-262).
 //
-// One thread per query with a private sorted list; queries are processed in cell order (sorted
-// by the caller) so the threads of a warp walk the same cells and their loads coalesce.
+// One thread per query with a private bounded heap in shared memory; queries are processed in
+// cell order (sorted by the caller) so the threads of a warp walk the same cells and their
+// loads coalesce.
 #include <float.h>
 #include <limits.h>
 
@@ -36,29 +37,59 @@ struct GridArgs {
   double h, inv_h;
 };
 
-template <int KMAX>
-struct TopKLex {
-  double dist[KMAX];
-  int idx[KMAX];
-  __device__ __forceinline__ void init(int k) {
-    for (int i = 0; i < k; ++i) {
-      dist[i] = DBL_MAX;
-      idx[i] = INT_MAX;
-    }
+// Per-query bounded MAX-heap on the key (distance, train row), resident in SHARED memory
+// (element i of thread t at [i * NT + t]: the lanes of a warp sit at different heap positions
+// but always in different banks).  Per-thread arrays in local memory spilled to L2 -- 1.5 MB of
+// lists per SM -- and every shift of the sorted insertion was an L2 round trip; the heap needs
+// log2(k) shared-memory steps per accepted candidate.  The root is the current worst entry.
+struct SmemHeap {
+  double* hd;
+  int* hi;
+  int nt, t;
+  __device__ __forceinline__ double& D(int i) { return hd[i * nt + t]; }
+  __device__ __forceinline__ int& I(int i) { return hi[i * nt + t]; }
+  static __device__ __forceinline__ bool less(double da, int ia, double db, int ib) {
+    return da < db || (da == db && ia < ib);
   }
-  __device__ __forceinline__ bool better(double dv, int iv, int k) const {
-    return dv < dist[k - 1] || (dv == dist[k - 1] && iv < idx[k - 1]);
-  }
-  // candidates arrive in arbitrary index order: order by (distance, index)
-  __device__ __forceinline__ void push(int k, double dv, int iv) {
-    int pos = k - 1;
-    while (pos > 0 && (dist[pos - 1] > dv || (dist[pos - 1] == dv && idx[pos - 1] > iv))) {
-      dist[pos] = dist[pos - 1];
-      idx[pos] = idx[pos - 1];
-      --pos;
+  // heap of `size` < k entries: add (s, id)
+  __device__ __forceinline__ void push(int size, double s, int id) {
+    int i = size;
+    while (i > 0) {
+      const int p = (i - 1) >> 1;
+      const double dp = D(p);
+      const int ip = I(p);
+      if (!less(dp, ip, s, id)) break;
+      D(i) = dp;
+      I(i) = ip;
+      i = p;
     }
-    dist[pos] = dv;
-    idx[pos] = iv;
+    D(i) = s;
+    I(i) = id;
+  }
+  // replace the root of a heap of `size` entries by (s, id) and restore the heap
+  __device__ __forceinline__ void replace_root(int size, double s, int id) {
+    int i = 0;
+    for (;;) {
+      int c = 2 * i + 1;
+      if (c >= size) break;
+      double dc = D(c);
+      int ic = I(c);
+      if (c + 1 < size) {
+        const double d2 = D(c + 1);
+        const int i2 = I(c + 1);
+        if (less(dc, ic, d2, i2)) {
+          dc = d2;
+          ic = i2;
+          ++c;
+        }
+      }
+      if (!less(s, id, dc, ic)) break;
+      D(i) = dc;
+      I(i) = ic;
+      i = c;
+    }
+    D(i) = s;
+    I(i) = id;
   }
 };
 
@@ -81,12 +112,18 @@ __global__ void grid_cell_ids_kernel(const double* __restrict__ pts, long long n
   }
 }
 
-template <int D, int KMAX>
-__global__ void __launch_bounds__(128) knn_grid_kernel(const GridArgs g) {
+template <int D>
+__global__ void knn_grid_kernel(const GridArgs g) {
+  extern __shared__ double heap_smem[];
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= g.q) return;
   const long long qi = g.order ? g.order[t] : t;
   const int k = g.k;
+  SmemHeap top;
+  top.hd = heap_smem;
+  top.hi = reinterpret_cast<int*>(heap_smem + (size_t)k * blockDim.x);
+  top.nt = blockDim.x;
+  top.t = threadIdx.x;
   double x[D];
   int c[D];
 #pragma unroll
@@ -95,8 +132,9 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const GridArgs g) {
     c[f] = cell_coord<D>(x[f], g.origin[f], g.inv_h, g.dims[f]);
   }
   const long long self = g.self_idx ? g.self_idx[qi] : -1;
-  TopKLex<KMAX> top;
-  top.init(k);
+  int size = 0;                            // heap entries so far (<= k)
+  double worst_d = DBL_MAX;                // the root once the heap is full
+  int worst_i = INT_MAX;
   int maxr = 0;
 #pragma unroll
   for (int f = 0; f < D; ++f) maxr = max(maxr, max(c[f], g.dims[f] - 1 - c[f]));
@@ -127,9 +165,20 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const GridArgs g) {
               const double df = __dsub_rn(x[f], g.pts[(long long)p * D + f]);
               s = __dadd_rn(s, __dmul_rn(df, df));
             }
-            if (s <= top.dist[k - 1]) {
+            if (s <= worst_d) {
               const int id = g.ids[p];
-              if (id != self && top.better(s, id, k)) top.push(k, s, id);
+              if (id == self) continue;
+              if (size < k) {
+                top.push(size, s, id);
+                if (++size == k) {
+                  worst_d = top.D(0);
+                  worst_i = top.I(0);
+                }
+              } else if (SmemHeap::less(s, id, worst_d, worst_i)) {
+                top.replace_root(k, s, id);
+                worst_d = top.D(0);
+                worst_i = top.I(0);
+              }
             }
           }
         }
@@ -145,23 +194,32 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const GridArgs g) {
     if (gap == DBL_MAX) break;  // the whole grid has been visited
     // guard the bound against rounding of the cell edges; stop only when strictly inside
     gap = gap * (1.0 - 1e-12) - 1e-300;
-    if (gap > 0.0 && top.dist[k - 1] < gap * gap) break;
+    if (gap > 0.0 && worst_d < gap * gap) break;
+  }
+  // heap sort in place: the root (largest key) moves behind the shrinking heap
+  for (int m = size - 1; m > 0; --m) {
+    const double s = top.D(m);
+    const int id = top.I(m);
+    top.D(m) = top.D(0);
+    top.I(m) = top.I(0);
+    top.replace_root(m, s, id);
   }
   for (int i = 0; i < k; ++i) {
-    g.out_idx[qi * k + i] = top.idx[i];
-    g.out_d2[qi * k + i] = top.dist[i];
+    g.out_idx[qi * k + i] = i < size ? top.I(i) : INT_MAX;
+    g.out_d2[qi * k + i] = i < size ? top.D(i) : DBL_MAX;
   }
 }
 
 template <int D>
 static int launch_grid(const GridArgs& g, cudaStream_t s) {
-  const unsigned blocks = (unsigned)((g.q + 127) / 128);
-  if (g.k <= 64)
-    knn_grid_kernel<D, 64><<<blocks, 128, 0, s>>>(g);
-  else if (g.k <= 128)
-    knn_grid_kernel<D, 128><<<blocks, 128, 0, s>>>(g);
-  else
-    knn_grid_kernel<D, 256><<<blocks, 128, 0, s>>>(g);
+  // threads per CTA: as many as keep several CTAs' heaps (12 bytes per entry) resident
+  int nt = 128;
+  while (nt > 32 && (size_t)nt * g.k * 12 > 40 * 1024) nt >>= 1;
+  const size_t smem = (size_t)nt * g.k * 12 + 8;
+  cudaFuncSetAttribute(knn_grid_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)max_smem_optin());
+  const unsigned blocks = (unsigned)((g.q + nt - 1) / nt);
+  knn_grid_kernel<D><<<blocks, nt, smem, s>>>(g);
   return check_launch("knn_grid_kernel");
 }
 

@@ -1,8 +1,9 @@
 // K2 (high-dimensional variant): exact brute-force KNN for d > 8 with register tiling.
 //
 // A CTA owns 64 queries and sweeps the training set in tiles of 64 points; each of the 256
-// threads accumulates a 4x4 block of squared distances over feature chunks staged in shared
-// memory, so every staged value feeds four subtractions.  Distances are accumulated feature by
+// threads accumulates a 4x4 block of squared distances (queries 4 ty + i, points tx + 16 j: with
+// the odd row pitch the 16 point rows a half-warp reads land in 16 different banks) over
+// feature chunks staged in shared memory, so every staged value feeds four subtractions.  Distances are accumulated feature by
 // feature in ascending order with separately rounded subtract / multiply / add -- the same
 // arithmetic, in the same order, as a scalar CPU loop and as the small-d kernel -- which makes
 // the ranking (ties to the lower train row) bit-identical to the oracle's.  This is why the
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(
 #pragma unroll
         for (int i = 0; i < 4; ++i) qv[i] = Qs[(ty * 4 + i) * KT_LD + f];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) xv[j] = Xs[(tx * 4 + j) * KT_LD + f];
+        for (int j = 0; j < 4; ++j) xv[j] = Xs[(tx + 16 * j) * KT_LD + f];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) Ds[(ty * 4 + i) * (KT_X + 1) + tx * 4 + j] = acc[i][j];
+      for (int j = 0; j < 4; ++j) Ds[(ty * 4 + i) * (KT_X + 1) + tx + 16 * j] = acc[i][j];
     __syncthreads();
     if (owner) {
       const int cnt = (int)min((long long)KT_X, x_end - x0);
