@@ -126,7 +126,12 @@ __global__ void __launch_bounds__(128) knn_warp_kernel(
 size_t knn_tiled_workspace_bytes(long long n, long long q, int k);
 int launch_knn_tiled(const double* train, long long n, const double* queries, long long q, int d,
                      int k, const int64_t* self_idx, int64_t* out_idx, double* out_d2, void* ws,
-                     size_t ws_bytes, cudaStream_t s);
+                     size_t ws_bytes, cudaStream_t s, const int32_t* qmap, const int32_t* qcount);
+bool knn_gram_supported(long long n, long long q, int d, int k);
+size_t knn_gram_workspace_bytes(long long n, long long q, int k);
+int launch_knn_gram(const double* train, long long n, const double* queries, long long q, int d,
+                    int k, const int64_t* self_idx, int64_t* out_idx, double* out_d2, void* ws,
+                    size_t ws_bytes, cudaStream_t s);
 
 template <int KMAX>
 static int launch_knn(const double* train, long long n, const double* queries, long long q,
@@ -170,6 +175,7 @@ using namespace mgp;
 
 extern "C" size_t mgp_knn_workspace_bytes(int64_t n, int64_t q, int32_t d, int32_t k) {
   if (d <= 8 || n < 1 || q < 8 || k < 1) return 0;
+  if (mgp::knn_gram_supported(n, q, d, k)) return mgp::knn_gram_workspace_bytes(n, q, k);
   return mgp::knn_tiled_workspace_bytes(n, q, k);
 }
 
@@ -190,8 +196,14 @@ extern "C" int mgp_knn(const double* train, int64_t n, const double* queries, in
   MGP_REQUIRE(!exclude_self || self_idx, MGP_ERR_BAD_ARG, "exclude_self needs self_idx");
   const int64_t* self = exclude_self ? self_idx : nullptr;
   cudaStream_t s = (cudaStream_t)stream;
-  if (d > 8 && q >= 8)  // register-tiled sweep; a handful of queries take the warp kernel
-    return launch_knn_tiled(train, n, queries, q, d, k, self, out_idx, out_d2, ws, ws_bytes, s);
+  if (d > 8 && q >= 8) {
+    // DMMA pre-filter + certified exact re-rank where it pays, else the register-tiled exact
+    // sweep; a handful of queries take the warp kernel
+    if (knn_gram_supported(n, q, d, k))
+      return launch_knn_gram(train, n, queries, q, d, k, self, out_idx, out_d2, ws, ws_bytes, s);
+    return launch_knn_tiled(train, n, queries, q, d, k, self, out_idx, out_d2, ws, ws_bytes, s,
+                            nullptr, nullptr);
+  }
   if (k <= 64) return launch_knn<64>(train, n, queries, q, d, k, self, out_idx, out_d2, s);
   if (k <= 128) return launch_knn<128>(train, n, queries, q, d, k, self, out_idx, out_d2, s);
   return launch_knn<256>(train, n, queries, q, d, k, self, out_idx, out_d2, s);

@@ -1,0 +1,528 @@
+// K2 (high-dimensional fast path): exact KNN for d > 8 as DMMA pre-filter + exact re-rank.
+//
+// The exact kernel (knn_tiled.cu) spends 3 FP64 issue slots per (query, point, feature) because
+// the ranking must reproduce a scalar CPU loop bit for bit (separately rounded subtract,
+// multiply, add).  Almost all of that work ranks points that are nowhere near the k-th
+// neighbour.  Here
+//
+//   1. knn_gram_filter_kernel sweeps the training set with FP64 tensor-core tiles,
+//      S~(q,x) = |q|^2 + |x|^2 - 2 q.x  (mma.sync.m8n8k4.f64, 1/8 issue slot per pair-feature),
+//      and keeps the K' = k + 8 smallest S~ per query;
+//   2. knn_gram_refine_kernel recomputes the K' candidates with the exact arithmetic of
+//      knn_tiled.cu / knn.cu (same operations, same feature order), ranks them by
+//      (distance, train row) and CERTIFIES the result: every point that is not a candidate has
+//      S~ >= tau (the largest kept S~), and |S~ - S| <= E with a rigorous rounding bound E, so
+//      its exact distance is at least L = tau - E.  If the exact k-th distance is strictly
+//      below L the k results are exactly what the full sweep returns (all ties included);
+//   3. queries that cannot be certified (near-ties across the candidate boundary, massive
+//      duplicates) are listed and re-run through the exact sweep (knn_tiled.cu, query map).
+//
+// So the returned indices and squared distances are always bit-identical to the brute-force
+// kernels'; only the amount of work depends on the data.
+#include <float.h>
+#include <limits.h>
+
+#include <cstdint>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace mgp {
+
+size_t knn_tiled_workspace_bytes(long long n, long long q, int k);
+int launch_knn_tiled(const double* train, long long n, const double* queries, long long q, int d,
+                     int k, const int64_t* self_idx, int64_t* out_idx, double* out_d2, void* ws,
+                     size_t ws_bytes, cudaStream_t s, const int32_t* qmap, const int32_t* qcount);
+
+namespace {
+
+constexpr int KG_Q = 64;     // queries per CTA
+constexpr int KG_X = 64;     // train points per tile
+constexpr int KG_F = 32;     // features per staged chunk
+constexpr int KG_LD = 36;    // row pitch: fragment loads (row rho, feature q4) hit 4 rho + q4
+constexpr int KG_MARGIN = 8; // extra candidates beyond k
+constexpr int KG_KMAX = 96;  // candidate list capacity
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// |row|^2 for every row (one warp per row) and, optionally, the maximum over rows
+__global__ void row_norms_kernel(const double* __restrict__ a, long long rows, int d,
+                                 double* __restrict__ out, unsigned long long* max_bits) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  double mx = 0.0;
+  for (long long r = w; r < rows; r += nw) {
+    double s = 0.0;
+    for (int f = lane; f < d; f += 32) {
+      const double v = a[r * d + f];
+      s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[r] = s;
+    mx = fmax(mx, s);
+  }
+  // non-negative doubles order like their bit patterns
+  if (max_bits && lane == 0 && mx > 0.0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+__device__ __forceinline__ void kg_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void kg_cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+
+// VEC: d even and both arrays 16-byte aligned -> 16-byte asynchronous copies
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
+    const double* __restrict__ train, long long n, const double* __restrict__ queries,
+    long long q, int d, int kk, const int64_t* __restrict__ self_idx,
+    const double* __restrict__ xn, const double* __restrict__ qn, long long split_len,
+    int nsplit, int32_t* __restrict__ part_idx, double* __restrict__ part_s,
+    int64_t* __restrict__ cand_idx, double* __restrict__ cand_s) {
+  // two staging buffers filled with cp.async (the copy of chunk t + 1 runs under the DMMAs of
+  // chunk t); the 64 x 65 tile of S~ reuses the buffer that was consumed last
+  extern __shared__ double stage[];
+  __shared__ double worst_sh[KG_Q];
+  __shared__ __align__(8) unsigned short mask_sh[4 * KG_Q];
+  constexpr int BUF = 2 * KG_Q * KG_LD;
+  static_assert(KG_Q * (KG_X + 1) <= BUF, "S~ tile must fit one staging buffer");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rho = lane >> 2, q4 = lane & 3;
+  const int tr0 = 2 * (warp & 3);   // this warp's two tile rows (queries)
+  const int tc0 = 4 * (warp >> 2);  // and four tile columns (train points)
+  const long long q0 = (long long)blockIdx.x * KG_Q;
+
+  // Candidate lists (sorted by S~) of the 64 queries live in shared memory, entry-major
+  // ([entry][query]: the owners' accesses never conflict).  As per-thread arrays they sat in
+  // local memory, and with the L1 carved down to ~30 KB by the staging buffers every shift of
+  // an insertion was an L2 round trip (ncu: 2/3 of all warp time went to the insertion loop
+  // and to the other six warps waiting for it at the barrier).
+  double* list_s = stage + 2 * BUF;
+  int* list_i = reinterpret_cast<int*>(list_s + (size_t)kk * KG_Q);
+#define BEST_S(i) list_s[(i) * KG_Q + tid]
+#define BEST_I(i) list_i[(i) * KG_Q + tid]
+  const bool owner = tid < KG_Q && q0 + tid < q;
+  long long self = -1;
+  if (owner) {
+    for (int i = 0; i < kk; ++i) {
+      BEST_S(i) = DBL_MAX;
+      BEST_I(i) = INT_MAX;
+    }
+    if (self_idx) self = self_idx[q0 + tid];
+  }
+  double worst = DBL_MAX;
+  double qnr[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const long long r = q0 + 8 * (tr0 + i) + rho;
+    qnr[i] = r < q ? qn[r] : 0.0;
+  }
+
+  const long long x_begin = (long long)blockIdx.y * split_len;
+  const long long x_end = min(n, x_begin + split_len);
+  const int nchunks = (d + KG_F - 1) / KG_F;
+  const long long ntiles = x_end > x_begin ? (x_end - x_begin + KG_X - 1) / KG_X : 0;
+  const long long total = ntiles * nchunks;
+
+  // a stage = one feature chunk of one train tile (and of the queries); stages run tile by
+  // tile, chunk by chunk (counters are kept incrementally: no 64-bit divisions in the loop)
+  auto issue = [&](long long x0, int f0, int buf) {
+    const int fc = min(KG_F, d - f0);
+    double* Qs = stage + buf * BUF;
+    double* Xs = Qs + KG_Q * KG_LD;
+    if (VEC) {
+      for (int e = tid; e < KG_Q * (KG_F / 2); e += 256) {
+        const int r = e / (KG_F / 2), f = 2 * (e - r * (KG_F / 2));
+        const long long qi = q0 + r, xi = x0 + r;
+        if (qi < q && f < fc) kg_cp_async16(&Qs[r * KG_LD + f], &queries[qi * d + f0 + f]);
+        else *reinterpret_cast<double2*>(&Qs[r * KG_LD + f]) = make_double2(0.0, 0.0);
+        if (xi < x_end && f < fc) kg_cp_async16(&Xs[r * KG_LD + f], &train[xi * d + f0 + f]);
+        else *reinterpret_cast<double2*>(&Xs[r * KG_LD + f]) = make_double2(0.0, 0.0);
+      }
+    } else {
+      for (int e = tid; e < KG_Q * KG_F; e += 256) {
+        const int r = e / KG_F, f = e - r * KG_F;
+        const long long qi = q0 + r, xi = x0 + r;
+        if (qi < q && f < fc) kg_cp_async8(&Qs[r * KG_LD + f], &queries[qi * d + f0 + f]);
+        else Qs[r * KG_LD + f] = 0.0;
+        if (xi < x_end && f < fc) kg_cp_async8(&Xs[r * KG_LD + f], &train[xi * d + f0 + f]);
+        else Xs[r * KG_LD + f] = 0.0;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  double acc[2][4][2];
+  if (total > 0) issue(x_begin, 0, 0);
+  long long x0 = x_begin;  // current stage
+  int chunk = 0, buf = 0;
+  for (long long st = 0; st < total; ++st, buf ^= 1) {
+    // the stage after this one
+    int nchunk = chunk + 1;
+    long long nx0 = x0;
+    if (nchunk == nchunks) {
+      nchunk = 0;
+      nx0 += KG_X;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();  // this stage has landed; nobody still reads the other buffer
+    if (st + 1 < total) issue(nx0, nchunk * KG_F, buf ^ 1);
+    if (chunk == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
+    const double* Qs = stage + buf * BUF;
+    const double* Xs = Qs + KG_Q * KG_LD;
+    const int ksteps = (min(KG_F, d - chunk * KG_F) + 3) >> 2;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      double a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = Qs[(8 * (tr0 + i) + rho) * KG_LD + 4 * ks + q4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Xs[(8 * (tc0 + j) + rho) * KG_LD + 4 * ks + q4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (chunk != nchunks - 1) {
+      chunk = nchunk;
+      continue;
+    }
+    // ---- a train tile is complete: S~ to the owners of the candidate lists ----------------
+    double* Ds = stage + buf * BUF;
+    __syncthreads();  // everyone is done with the staged features of this buffer
+    // accumulator layout: lane (rho, q4) holds columns 2 q4, 2 q4 + 1 of row rho
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 8 * (tc0 + j) + 2 * q4;
+      const double xn0 = (x0 + c < x_end) ? xn[x0 + c] : 0.0;
+      const double xn1 = (x0 + c + 1 < x_end) ? xn[x0 + c + 1] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = 8 * (tr0 + i) + rho;
+        Ds[r * (KG_X + 1) + c] = fma(-2.0, acc[i][j][0], qnr[i] + xn0);
+        Ds[r * (KG_X + 1) + c + 1] = fma(-2.0, acc[i][j][1], qnr[i] + xn1);
+      }
+    }
+    if (owner) worst_sh[tid] = worst;
+    __syncthreads();
+    // All 256 threads screen the tile against the owners' current thresholds (thread t: query
+    // t / 4, 16 candidates) and leave a bit mask of survivors; the owner of a query then only
+    // visits the set bits (a handful per tile once the lists have warmed up), in ascending
+    // candidate order, re-testing against its tightening threshold.
+    {
+      const int r = tid >> 2, c0 = (tid & 3) * 16;
+      const double w = worst_sh[r];
+      const int cnt = (int)min((long long)KG_X, x_end - x0);
+      unsigned m = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c0 + j < cnt && Ds[r * (KG_X + 1) + c0 + j] < w) m |= 1u << j;
+      mask_sh[tid] = (unsigned short)m;
+    }
+    __syncthreads();
+    if (owner) {
+      unsigned long long m = *reinterpret_cast<const unsigned long long*>(&mask_sh[4 * tid]);
+      while (m) {
+        const int j = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const double s = Ds[tid * (KG_X + 1) + j];
+        if (s < worst && x0 + j != self) {
+          int pos = kk - 1;
+          while (pos > 0) {
+            const double prev = BEST_S(pos - 1);
+            if (!(prev > s)) break;
+            BEST_S(pos) = prev;
+            BEST_I(pos) = BEST_I(pos - 1);
+            --pos;
+          }
+          BEST_S(pos) = s;
+          BEST_I(pos) = (int)(x0 + j);
+          worst = BEST_S(kk - 1);
+        }
+      }
+    }
+    // (the next iteration's barrier keeps this buffer from being refilled under the scan)
+    chunk = nchunk;
+    x0 = nx0;
+  }
+  if (owner) {
+    if (nsplit == 1) {
+      for (int i = 0; i < kk; ++i) {
+        cand_idx[(q0 + tid) * kk + i] = BEST_I(i);
+        cand_s[(q0 + tid) * kk + i] = BEST_S(i);
+      }
+    } else {
+      const long long base = ((q0 + tid) * nsplit + blockIdx.y) * kk;
+      for (int i = 0; i < kk; ++i) {
+        part_idx[base + i] = BEST_I(i);
+        part_s[base + i] = BEST_S(i);
+      }
+    }
+  }
+#undef BEST_S
+#undef BEST_I
+}
+
+// merge the per-slice candidate lists of one query (lists sorted by S~)
+template <int KMAX>
+__global__ void knn_gram_merge_kernel(const int32_t* __restrict__ part_idx,
+                                      const double* __restrict__ part_s, long long q, int nsplit,
+                                      int kk, int64_t* __restrict__ cand_idx,
+                                      double* __restrict__ cand_s) {
+  const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (qi >= q) return;
+  double best_s[KMAX];
+  int best_i[KMAX];
+  for (int i = 0; i < kk; ++i) {
+    best_s[i] = DBL_MAX;
+    best_i[i] = INT_MAX;
+  }
+  for (int s = 0; s < nsplit; ++s) {
+    const long long base = (qi * nsplit + s) * kk;
+    for (int j = 0; j < kk; ++j) {
+      const double dv = part_s[base + j];
+      if (!(dv < best_s[kk - 1])) break;
+      int pos = kk - 1;
+      while (pos > 0 && best_s[pos - 1] > dv) {
+        best_s[pos] = best_s[pos - 1];
+        best_i[pos] = best_i[pos - 1];
+        --pos;
+      }
+      best_s[pos] = dv;
+      best_i[pos] = part_idx[base + j];
+    }
+  }
+  for (int i = 0; i < kk; ++i) {
+    cand_idx[qi * kk + i] = best_i[i];
+    cand_s[qi * kk + i] = best_s[i];
+  }
+}
+
+// One warp per query: exact distances of the kk candidates (the arithmetic of knn_tiled.cu),
+// rank by (distance, row), certify against the pre-filter's threshold.
+__global__ void __launch_bounds__(128) knn_gram_refine_kernel(
+    const double* __restrict__ train, long long n, const double* __restrict__ queries,
+    long long q, int d, int k, int kk, const int64_t* __restrict__ cand_idx,
+    const double* __restrict__ cand_s, const double* __restrict__ qn,
+    const unsigned long long* __restrict__ xn_max_bits, int64_t* __restrict__ out_idx,
+    double* __restrict__ out_d2, int32_t* __restrict__ flag_list, int32_t* __restrict__ flag_count) {
+  __shared__ double rows[4][32 * 33];
+  __shared__ double sd[4][KG_KMAX];
+  __shared__ int si[4][KG_KMAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long qi = blockIdx.x * 4LL + warp;
+  if (qi >= q) return;
+  double* buf = rows[warp];
+  const double* qrow = queries + qi * d;
+  for (int g0 = 0; g0 < kk; g0 += 32) {
+    const int c = g0 + lane;
+    const long long my = c < kk ? cand_idx[qi * kk + c] : -1;
+    const int cnt = min(32, kk - g0);
+    double acc = 0.0;
+    for (int f0 = 0; f0 < d; f0 += 32) {
+      const double qreg = (f0 + lane < d) ? qrow[f0 + lane] : 0.0;
+      __syncwarp();
+      for (int c2 = 0; c2 < cnt; ++c2) {
+        const long long src = __shfl_sync(0xffffffffu, my, c2);
+        buf[c2 * 33 + lane] = (f0 + lane < d) ? train[src * d + f0 + lane] : 0.0;
+      }
+      __syncwarp();
+      // every lane runs the loop (the query chunk is broadcast with full-warp shuffles); lanes
+      // without a candidate accumulate stale rows and are ignored below
+#pragma unroll 8
+      for (int f = 0; f < 32; ++f) {
+        const double df = __dsub_rn(__shfl_sync(0xffffffffu, qreg, f), buf[lane * 33 + f]);
+        acc = __dadd_rn(acc, __dmul_rn(df, df));
+      }
+    }
+    if (c < kk) {
+      sd[warp][c] = acc;
+      si[warp][c] = (int)my;
+    }
+  }
+  __syncwarp();
+  // rank every candidate among all candidates by (distance, row)
+  bool certified = true;
+  for (int c = lane; c < kk; c += 32) {
+    const double ms = sd[warp][c];
+    const int mi = si[warp][c];
+    int rank = 0;
+    for (int j = 0; j < kk; ++j) {
+      const double os = sd[warp][j];
+      const int oi = si[warp][j];
+      rank += (os < ms || (os == ms && oi < mi)) ? 1 : 0;
+    }
+    if (rank < k) {
+      out_idx[qi * k + rank] = mi;
+      out_d2[qi * k + rank] = ms;
+    }
+    if (rank == k - 1 && (long long)kk < n) {
+      // Non-candidates have S~ >= tau.  |S~ - S| <= gamma (|q|^2 + |x|^2 + 2|q.x|)
+      // <= 2 gamma (|q|^2 + |x|^2) with gamma ~ (d + 2) 2^-53 for the norms and the DMMA dot
+      // product; the brute-force sum itself is within d 2^-53 relative of S.  Use 8x that.
+      const double tau = cand_s[qi * kk + kk - 1];
+      const double gamma = 8.0 * (double)(d + 8) * 1.1102230246251565e-16;
+      const double xmax = __longlong_as_double((long long)*xn_max_bits);
+      const double lower = (tau - 2.0 * gamma * (qn[qi] + xmax)) * (1.0 - gamma);
+      certified = ms < lower;
+    }
+  }
+  if (!certified) {
+    const int pos = atomicAdd(flag_count, 1);
+    flag_list[pos] = (int32_t)qi;
+  }
+}
+
+struct GramWs {
+  double* xn;
+  double* qn;
+  unsigned long long* xn_max;
+  int32_t* flag_count;
+  int32_t* flag_list;
+  int64_t* cand_idx;
+  double* cand_s;
+  double* part_s;
+  int32_t* part_idx;
+  void* tiled_ws;
+  size_t tiled_bytes;
+  size_t total;
+};
+
+// slices of the training set per query block: enough CTAs for ~4 full waves of 2 CTAs per SM,
+// at least 4096 points per slice, and the count whose last wave is fullest
+int gram_splits(long long n, long long q) {
+  const long long qblocks = (q + KG_Q - 1) / KG_Q;
+  const long long wave = 2LL * sm_count();
+  long long hi = (n + 4095) / 4096;
+  if (hi > 64) hi = 64;
+  if (hi < 1) hi = 1;
+  long long lo = (wave + qblocks - 1) / qblocks;
+  if (lo > hi) lo = hi;
+  long long best = lo;
+  double best_eff = 0.0;
+  for (long long ns = lo; ns <= hi; ++ns) {
+    const long long ctas = qblocks * ns;
+    const double eff = (double)ctas / (double)(((ctas + wave - 1) / wave) * wave);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = ns;
+    }
+    if (ctas >= 4 * wave && eff > 0.95) break;
+  }
+  return (int)best;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+GramWs carve(void* ws, long long n, long long q, int k, int kk) {
+  GramWs w;
+  const int ns = gram_splits(n, q);
+  char* p = (char*)ws;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align256(bytes);
+    return r;
+  };
+  w.xn = (double*)take((size_t)n * 8);
+  w.qn = (double*)take((size_t)q * 8);
+  w.xn_max = (unsigned long long*)take(16);
+  w.flag_count = (int32_t*)(w.xn_max ? (char*)w.xn_max + 8 : nullptr);
+  w.flag_list = (int32_t*)take((size_t)q * 4);
+  w.cand_idx = (int64_t*)take((size_t)q * kk * 8);
+  w.cand_s = (double*)take((size_t)q * kk * 8);
+  w.part_s = (double*)take(ns > 1 ? (size_t)q * ns * kk * 8 : 0);
+  w.part_idx = (int32_t*)take(ns > 1 ? (size_t)q * ns * kk * 4 : 0);
+  w.tiled_bytes = knn_tiled_workspace_bytes(n, q, k);
+  w.tiled_ws = take(w.tiled_bytes);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+static const bool g_knn_gram_off = getenv("MGP_NO_GRAM_KNN") != nullptr;  // dev switch
+
+bool knn_gram_supported(long long n, long long q, int d, int k) {
+  if (g_knn_gram_off) return false;
+  // below ~32 features the exact sweep is already cheap relative to the candidate bookkeeping
+  return d >= 32 && q >= 8 && n >= 2048 && k + KG_MARGIN <= KG_KMAX;
+}
+
+static int gram_kk(long long n, int k, bool has_self) {
+  long long kk = k + KG_MARGIN;
+  const long long avail = n - (has_self ? 1 : 0);
+  if (kk > avail) kk = avail;
+  return (int)kk;
+}
+
+size_t knn_gram_workspace_bytes(long long n, long long q, int k) {
+  return carve(nullptr, n, q, k, k + KG_MARGIN).total + 256;
+}
+
+int launch_knn_gram(const double* train, long long n, const double* queries, long long q, int d,
+                    int k, const int64_t* self_idx, int64_t* out_idx, double* out_d2, void* ws,
+                    size_t ws_bytes, cudaStream_t s) {
+  MGP_REQUIRE(ws != nullptr && ws_bytes >= knn_gram_workspace_bytes(n, q, k), MGP_ERR_WORKSPACE,
+              "KNN workspace too small (%zu bytes)", ws_bytes);
+  const int kk = gram_kk(n, k, self_idx != nullptr);
+  void* base = (void*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  const GramWs w = carve(base, n, q, k, k + KG_MARGIN);
+  const int ns = gram_splits(n, q);
+  cudaMemsetAsync(w.xn_max, 0, 16, s);
+  const int nb = sm_count() * 8;
+  row_norms_kernel<<<nb, 256, 0, s>>>(train, n, d, w.xn, w.xn_max);
+  row_norms_kernel<<<nb, 256, 0, s>>>(queries, q, d, w.qn, nullptr);
+  long long split_len = (n + ns - 1) / ns;
+  split_len = (split_len + KG_X - 1) / KG_X * KG_X;
+  const dim3 grid((unsigned)((q + KG_Q - 1) / KG_Q), (unsigned)ns);
+  const size_t kg_smem = 2 * 2 * KG_Q * KG_LD * sizeof(double) + (size_t)kk * KG_Q * 12;
+  const bool vec = d % 2 == 0 && (uintptr_t)train % 16 == 0 && (uintptr_t)queries % 16 == 0;
+  if (vec) {
+    cudaFuncSetAttribute(knn_gram_filter_kernel<true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem);
+    knn_gram_filter_kernel<true><<<grid, 256, kg_smem, s>>>(
+        train, n, queries, q, d, kk, self_idx, w.xn, w.qn, split_len, ns, w.part_idx, w.part_s,
+        w.cand_idx, w.cand_s);
+  } else {
+    cudaFuncSetAttribute(knn_gram_filter_kernel<false>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem);
+    knn_gram_filter_kernel<false><<<grid, 256, kg_smem, s>>>(
+        train, n, queries, q, d, kk, self_idx, w.xn, w.qn, split_len, ns, w.part_idx, w.part_s,
+        w.cand_idx, w.cand_s);
+  }
+  if (ns > 1) {
+    if (kk <= 48)
+      knn_gram_merge_kernel<48><<<(unsigned)((q + 127) / 128), 128, 0, s>>>(
+          w.part_idx, w.part_s, q, ns, kk, w.cand_idx, w.cand_s);
+    else
+      knn_gram_merge_kernel<KG_KMAX><<<(unsigned)((q + 127) / 128), 128, 0, s>>>(
+          w.part_idx, w.part_s, q, ns, kk, w.cand_idx, w.cand_s);
+  }
+  int rc = check_launch("knn_gram_filter_kernel");
+  if (rc != MGP_OK) return rc;
+  knn_gram_refine_kernel<<<(unsigned)((q + 3) / 4), 128, 0, s>>>(
+      train, n, queries, q, d, k, kk, w.cand_idx, w.cand_s, w.qn, w.xn_max, out_idx, out_d2,
+      w.flag_list, w.flag_count);
+  rc = check_launch("knn_gram_refine_kernel");
+  if (rc != MGP_OK) return rc;
+  // exact sweep for the queries that could not be certified (device-side count; CTAs beyond
+  // it exit immediately, so the common case costs one empty launch)
+  return launch_knn_tiled(train, n, queries, q, d, k, self_idx, out_idx, out_d2, w.tiled_ws,
+                          w.tiled_bytes, s, w.flag_list, w.flag_count);
+}
+
+}  // namespace mgp

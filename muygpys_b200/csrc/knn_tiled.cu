@@ -27,8 +27,13 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(
     const double* __restrict__ train, long long n, const double* __restrict__ queries,
     long long q, int d, int k, const int64_t* __restrict__ self_idx, long long split_len,
     int nsplit, int32_t* __restrict__ part_idx, double* __restrict__ part_d2,
-    int64_t* __restrict__ out_idx, double* __restrict__ out_d2) {
+    int64_t* __restrict__ out_idx, double* __restrict__ out_d2,
+    const int32_t* __restrict__ qmap, const int32_t* __restrict__ qcount) {
   __shared__ double stage[2 * KT_Q * KT_LD];
+  // optional indirection (re-run of the queries the Gram pre-filter could not certify):
+  // local query j is row qmap[j] of `queries` / `self_idx` / the outputs, *qcount of them
+  if (qcount) q = *qcount;
+  if ((long long)blockIdx.x * KT_Q >= q) return;
   double* Qs = stage;
   double* Xs = stage + KT_Q * KT_LD;
   double* Ds = stage;  // the 64 x 65 tile of squared distances reuses the staging area
@@ -41,13 +46,14 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(
   double best_d[KMAX];
   int best_i[KMAX];
   const bool owner = tid < KT_Q && q0 + tid < q;
+  const long long my_row = owner ? (qmap ? (long long)qmap[q0 + tid] : q0 + tid) : 0;
   long long self = -1;
   if (owner) {
     for (int i = 0; i < k; ++i) {
       best_d[i] = DBL_MAX;
       best_i[i] = INT_MAX;
     }
-    if (self_idx) self = self_idx[q0 + tid];
+    if (self_idx) self = self_idx[my_row];
   }
   double worst = DBL_MAX;
 
@@ -66,7 +72,8 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(
       for (int e = tid; e < KT_Q * KT_F; e += 256) {
         const int r = e / KT_F, f = e - r * KT_F;
         const long long qi = q0 + r, xi = x0 + r;
-        Qs[r * KT_LD + f] = (qi < q && f < fc) ? queries[qi * d + f0 + f] : 0.0;
+        const long long qrow = (qmap && qi < q) ? (long long)qmap[qi] : qi;
+        Qs[r * KT_LD + f] = (qi < q && f < fc) ? queries[qrow * d + f0 + f] : 0.0;
         Xs[r * KT_LD + f] = (xi < x_end && f < fc) ? train[xi * d + f0 + f] : 0.0;
       }
       __syncthreads();
@@ -112,8 +119,8 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(
   if (owner) {
     if (nsplit == 1) {
       for (int i = 0; i < k; ++i) {
-        out_idx[(q0 + tid) * k + i] = best_i[i];
-        out_d2[(q0 + tid) * k + i] = best_d[i];
+        out_idx[my_row * k + i] = best_i[i];
+        out_d2[my_row * k + i] = best_d[i];
       }
     } else {
       const long long base = ((q0 + tid) * nsplit + blockIdx.y) * k;
@@ -132,9 +139,12 @@ template <int KMAX>
 __global__ void knn_merge_kernel(const int32_t* __restrict__ part_idx,
                                  const double* __restrict__ part_d2, long long q, int nsplit,
                                  int k, int64_t* __restrict__ out_idx,
-                                 double* __restrict__ out_d2) {
+                                 double* __restrict__ out_d2, const int32_t* __restrict__ qmap,
+                                 const int32_t* __restrict__ qcount) {
   const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (qcount) q = *qcount;
   if (qi >= q) return;
+  const long long orow = qmap ? (long long)qmap[qi] : qi;
   double best_d[KMAX];
   int best_i[KMAX];
   for (int i = 0; i < k; ++i) {
@@ -157,8 +167,8 @@ __global__ void knn_merge_kernel(const int32_t* __restrict__ part_idx,
     }
   }
   for (int i = 0; i < k; ++i) {
-    out_idx[qi * k + i] = best_i[i];
-    out_d2[qi * k + i] = best_d[i];
+    out_idx[orow * k + i] = best_i[i];
+    out_d2[orow * k + i] = best_d[i];
   }
 }
 
@@ -177,9 +187,12 @@ size_t knn_tiled_workspace_bytes(long long n, long long q, int k) {
   return ns == 1 ? 0 : (size_t)q * ns * k * (sizeof(int32_t) + sizeof(double)) + 16;
 }
 
+// qmap / qcount (device, optional): run only the *qcount queries listed in qmap (the grid is
+// still sized for q; surplus CTAs exit at once)
 int launch_knn_tiled(const double* train, long long n, const double* queries, long long q, int d,
                      int k, const int64_t* self_idx, int64_t* out_idx, double* out_d2, void* ws,
-                     size_t ws_bytes, cudaStream_t s) {
+                     size_t ws_bytes, cudaStream_t s, const int32_t* qmap,
+                     const int32_t* qcount) {
   const int ns = tiled_splits(n, q);
   MGP_REQUIRE(ws_bytes >= knn_tiled_workspace_bytes(n, q, k) && (ns == 1 || ws != nullptr),
               MGP_ERR_WORKSPACE, "KNN workspace too small (%zu bytes)", ws_bytes);
@@ -191,10 +204,11 @@ int launch_knn_tiled(const double* train, long long n, const double* queries, lo
 #define MGP_KT(KM)                                                                            \
   do {                                                                                        \
     knn_tiled_kernel<KM><<<grid, 256, 0, s>>>(train, n, queries, q, d, k, self_idx, split_len, \
-                                              ns, part_idx, part_d2, out_idx, out_d2);        \
+                                              ns, part_idx, part_d2, out_idx, out_d2, qmap,   \
+                                              qcount);                                        \
     if (ns > 1)                                                                               \
-      knn_merge_kernel<KM><<<(unsigned)((q + 127) / 128), 128, 0, s>>>(part_idx, part_d2, q,  \
-                                                                       ns, k, out_idx, out_d2); \
+      knn_merge_kernel<KM><<<(unsigned)((q + 127) / 128), 128, 0, s>>>(                       \
+          part_idx, part_d2, q, ns, k, out_idx, out_d2, qmap, qcount);                        \
   } while (0)
   if (k <= 64)
     MGP_KT(64);

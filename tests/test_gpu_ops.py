@@ -444,3 +444,45 @@ def test_high_dimensional_gram_cancellation_fixup(kid):
     # rows 8..11 have Kcross ~ 0; compare them on the absolute scale of the others
     assert_close(out["mean"].cpu().numpy(), O.posterior_mean(pK, Kcross, y[nn]), 1e-9, "mean")
     assert_close(out["var"].cpu().numpy(), O.diagonal_variance(pK, Kcross), 1e-9, "var")
+
+
+@pytest.mark.parametrize("layout", ["random", "offset", "duplicates", "lattice"])
+def test_high_d_knn_gram_prefilter_is_exact(layout):
+    """d >= 32: the DMMA Gram pre-filter + certified exact re-rank (csrc/knn_gram.cu) must return
+    bit for bit what the exact sweep returns -- on random data, on data far from the origin
+    (large norms -> large cancellation bound), with every point repeated 12 times (ties straddle
+    the candidate boundary: certification fails and the exact sweep re-runs those queries) and
+    on an integer lattice where most distances are tied."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(len(layout))
+    n, q, d, k = 4_000, 150, 33, 41
+    if layout == "random":
+        x = rng.normal(size=(n, d))
+        qs = rng.normal(size=(q, d))
+    elif layout == "offset":
+        x = rng.normal(size=(n, d)) + 1e4
+        qs = rng.normal(size=(q, d)) + 1e4
+    elif layout == "duplicates":
+        base = rng.normal(size=(n // 12 + 1, d))
+        x = np.repeat(base, 12, axis=0)[:n]
+        qs = base[rng.integers(0, len(base), q)] + 1e-3 * rng.normal(size=(q, d))
+    else:
+        x = rng.integers(0, 2, size=(n, d)).astype(np.float64)
+        qs = rng.integers(0, 2, size=(q, d)).astype(np.float64)
+    xd, qd = dev(x), dev(qs)
+    for kk in (k, 88):
+        gi, gd = ops.knn(xd, qd, kk)
+        want_i, want_d = O.knn_exact(x, qs, kk, chunk=16)
+        np.testing.assert_array_equal(gi.cpu().numpy(), want_i)
+        np.testing.assert_array_equal(gd.cpu().numpy(), want_d)
+    rows = dev(rng.integers(0, n, 64))
+    si, sd = ops.knn(xd, xd[rows], k, self_idx=rows)
+    rn = rows.cpu().numpy()
+    dist = np.zeros((len(rn), n))
+    for f in range(d):  # the oracle's arithmetic: direct differences in feature order
+        dist += (x[rn, f:f + 1] - x[None, :, f]) ** 2
+    dist[np.arange(len(rn)), rn] = np.inf  # explicit self exclusion
+    order = np.argsort(dist, axis=1, kind="stable")[:, :k]
+    np.testing.assert_array_equal(si.cpu().numpy(), order)
+    np.testing.assert_array_equal(sd.cpu().numpy(), np.take_along_axis(dist, order, axis=1))
