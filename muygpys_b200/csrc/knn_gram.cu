@@ -26,6 +26,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "smem_heap.cuh"
 
 namespace mgp {
 
@@ -101,25 +102,22 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
   const int tc0 = 4 * (warp >> 2);  // and four tile columns (train points)
   const long long q0 = (long long)blockIdx.x * KG_Q;
 
-  // Candidate lists (sorted by S~) of the 64 queries live in shared memory, entry-major
-  // ([entry][query]: the owners' accesses never conflict).  As per-thread arrays they sat in
-  // local memory, and with the L1 carved down to ~30 KB by the staging buffers every shift of
-  // an insertion was an L2 round trip (ncu: 2/3 of all warp time went to the insertion loop
-  // and to the other six warps waiting for it at the barrier).
-  double* list_s = stage + 2 * BUF;
-  int* list_i = reinterpret_cast<int*>(list_s + (size_t)kk * KG_Q);
-#define BEST_S(i) list_s[(i) * KG_Q + tid]
-#define BEST_I(i) list_i[(i) * KG_Q + tid]
+  // The candidates of the 64 queries are bounded max-heaps on (S~, row) in shared memory,
+  // entry-major ([entry][query]: the owners' accesses never conflict).  As per-thread sorted
+  // arrays they sat in local memory, and with the L1 carved down to ~30 KB by the staging
+  // buffers every shift of an insertion was an L2 round trip (ncu: 2/3 of all warp time went to
+  // the insertion loop and to the other six warps waiting for it at the barrier).
+  SmemHeap top;
+  top.hd = stage + 2 * BUF;
+  top.hi = reinterpret_cast<int*>(top.hd + (size_t)kk * KG_Q);
+  top.nt = KG_Q;
+  top.t = tid;
   const bool owner = tid < KG_Q && q0 + tid < q;
   long long self = -1;
-  if (owner) {
-    for (int i = 0; i < kk; ++i) {
-      BEST_S(i) = DBL_MAX;
-      BEST_I(i) = INT_MAX;
-    }
-    if (self_idx) self = self_idx[q0 + tid];
-  }
-  double worst = DBL_MAX;
+  if (owner && self_idx) self = self_idx[q0 + tid];
+  int size = 0;             // heap entries so far (<= kk)
+  double worst = DBL_MAX;   // the root once the heap is full
+  int worst_i = INT_MAX;
   double qnr[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -229,7 +227,7 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
       unsigned m = 0;
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (c0 + j < cnt && Ds[r * (KG_X + 1) + c0 + j] < w) m |= 1u << j;
+        if (c0 + j < cnt && Ds[r * (KG_X + 1) + c0 + j] <= w) m |= 1u << j;
       mask_sh[tid] = (unsigned short)m;
     }
     __syncthreads();
@@ -239,18 +237,18 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
         const int j = __ffsll((long long)m) - 1;
         m &= m - 1;
         const double s = Ds[tid * (KG_X + 1) + j];
-        if (s < worst && x0 + j != self) {
-          int pos = kk - 1;
-          while (pos > 0) {
-            const double prev = BEST_S(pos - 1);
-            if (!(prev > s)) break;
-            BEST_S(pos) = prev;
-            BEST_I(pos) = BEST_I(pos - 1);
-            --pos;
+        const int id = (int)(x0 + j);
+        if (id == self) continue;
+        if (size < kk) {
+          top.push(size, s, id);
+          if (++size == kk) {
+            worst = top.D(0);
+            worst_i = top.I(0);
           }
-          BEST_S(pos) = s;
-          BEST_I(pos) = (int)(x0 + j);
-          worst = BEST_S(kk - 1);
+        } else if (SmemHeap::less(s, id, worst, worst_i)) {
+          top.replace_root(kk, s, id);
+          worst = top.D(0);
+          worst_i = top.I(0);
         }
       }
     }
@@ -259,21 +257,27 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
     x0 = nx0;
   }
   if (owner) {
+    // heap sort in place (ascending), then hand the list over; a short slice leaves sentinels
+    for (int m = size - 1; m > 0; --m) {
+      const double s = top.D(m);
+      const int id = top.I(m);
+      top.D(m) = top.D(0);
+      top.I(m) = top.I(0);
+      top.replace_root(m, s, id);
+    }
     if (nsplit == 1) {
       for (int i = 0; i < kk; ++i) {
-        cand_idx[(q0 + tid) * kk + i] = BEST_I(i);
-        cand_s[(q0 + tid) * kk + i] = BEST_S(i);
+        cand_idx[(q0 + tid) * kk + i] = i < size ? top.I(i) : INT_MAX;
+        cand_s[(q0 + tid) * kk + i] = i < size ? top.D(i) : DBL_MAX;
       }
     } else {
       const long long base = ((q0 + tid) * nsplit + blockIdx.y) * kk;
       for (int i = 0; i < kk; ++i) {
-        part_idx[base + i] = BEST_I(i);
-        part_s[base + i] = BEST_S(i);
+        part_idx[base + i] = i < size ? top.I(i) : INT_MAX;
+        part_s[base + i] = i < size ? top.D(i) : DBL_MAX;
       }
     }
   }
-#undef BEST_S
-#undef BEST_I
 }
 
 // merge the per-slice candidate lists of one query (lists sorted by S~)
@@ -402,7 +406,8 @@ struct GramWs {
 };
 
 // slices of the training set per query block: enough CTAs for ~4 full waves of 2 CTAs per SM,
-// at least 4096 points per slice, and the count whose last wave is fullest
+// at least 4096 points per slice (every slice warms up its own candidate heaps), and the count
+// whose last wave is fullest
 int gram_splits(long long n, long long q) {
   const long long qblocks = (q + KG_Q - 1) / KG_Q;
   const long long wave = 2LL * sm_count();
@@ -455,11 +460,13 @@ GramWs carve(void* ws, long long n, long long q, int k, int kk) {
 }  // namespace
 
 static const bool g_knn_gram_off = getenv("MGP_NO_GRAM_KNN") != nullptr;  // dev switch
+static const int g_knn_gram_min_d =
+    getenv("MGP_GRAM_KNN_MIN_D") ? atoi(getenv("MGP_GRAM_KNN_MIN_D")) : 9;  // dev switch
 
 bool knn_gram_supported(long long n, long long q, int d, int k) {
   if (g_knn_gram_off) return false;
-  // below ~32 features the exact sweep is already cheap relative to the candidate bookkeeping
-  return d >= 32 && q >= 8 && n >= 2048 && k + KG_MARGIN <= KG_KMAX;
+  // (measured: the pre-filter wins for every d > 8 -- 35 ms vs 97 ms at d = 9, 200 k x 20 k)
+  return d >= g_knn_gram_min_d && q >= 8 && n >= 2048 && k + KG_MARGIN <= KG_KMAX;
 }
 
 static int gram_kk(long long n, int k, bool has_self) {

@@ -446,17 +446,19 @@ def test_high_dimensional_gram_cancellation_fixup(kid):
     assert_close(out["var"].cpu().numpy(), O.diagonal_variance(pK, Kcross), 1e-9, "var")
 
 
-@pytest.mark.parametrize("layout", ["random", "offset", "duplicates", "lattice"])
-def test_high_d_knn_gram_prefilter_is_exact(layout):
-    """d >= 32: the DMMA Gram pre-filter + certified exact re-rank (csrc/knn_gram.cu) must return
+@pytest.mark.parametrize("layout,d", [("random", 33), ("offset", 33), ("duplicates", 33),
+                                      ("lattice", 33), ("random", 12), ("lattice", 9),
+                                      ("duplicates", 16)])
+def test_high_d_knn_gram_prefilter_is_exact(layout, d):
+    """d > 8: the DMMA Gram pre-filter + certified exact re-rank (csrc/knn_gram.cu) must return
     bit for bit what the exact sweep returns -- on random data, on data far from the origin
     (large norms -> large cancellation bound), with every point repeated 12 times (ties straddle
     the candidate boundary: certification fails and the exact sweep re-runs those queries) and
     on an integer lattice where most distances are tied."""
     from muygpys_b200 import ops
 
-    rng = np.random.default_rng(len(layout))
-    n, q, d, k = 4_000, 150, 33, 41
+    rng = np.random.default_rng(len(layout) + d)
+    n, q, k = 4_000, 150, 41
     if layout == "random":
         x = rng.normal(size=(n, d))
         qs = rng.normal(size=(q, d))
