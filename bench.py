@@ -293,6 +293,18 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e_evs)], device=dev)
+    # what the host link of this box gives for the same pinned index buffer (explains e2e)
+    nn_stage = torch.empty_like(nn)
+    nn_stage.copy_(nn_pin, non_blocking=True)
+    torch.cuda.synchronize()
+    ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ca.record()
+    for _ in range(5):
+        nn_stage.copy_(nn_pin, non_blocking=True)
+    cb.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 5 * nn_pin.numel() * 8 / (ca.elapsed_time(cb) * 1e-3) / 1e9
+    del nn_stage
 
     # ---- LOO-mse objective evaluations (second half of the BASELINE metric) -----------
     bi = torch.as_tensor(np.random.default_rng(50 + rank).choice(N_TRAIN, LOO_BATCH,
@@ -351,8 +363,13 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(q_pin.numel() * 8 + nn_pin.numel() * 8
                                               + idx_pin.numel() * 8),
                     "d2h_bytes_per_step": int(2 * N_TEST * 8),
-                    "api": "muygpys_b200.examples.from_indices.regress_from_indices, pinned "
-                           "host test features + int64 neighbour indices in, mean/var out"},
+                    "h2d_link_gbs": h2d_gbs,
+                    "h2d_ms_at_link_rate": (q_pin.numel() + nn_pin.numel() + idx_pin.numel())
+                    * 8 / h2d_gbs / 1e6,
+                    "api": "muygpys_b200.examples.from_indices.regress_from_indices -> "
+                           "mgp_fused_posterior_host (chunked copy/compute pipeline in the "
+                           "C-ABI library); pinned host test features + int64 neighbour "
+                           "indices in, mean/var out"},
             "gpu_launches": args.steps,  # one fused_tile_kernel launch per timed step per rank
             "clocks": clocks,
             "roofline": {

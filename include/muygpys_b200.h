@@ -124,6 +124,19 @@ const char* mgp_last_error(void);
 size_t mgp_fused_workspace_bytes(const mgp_problem* p);
 int mgp_fused_posterior(const mgp_problem* p, void* ws, size_t ws_bytes, void* stream);
 
+/* Host-buffer form of the same call -- what `regress_from_indices`
+ * (MuyGPyS/examples/from_indices.py:22-63) is handed: neighbour indices (and batch indices) in
+ * HOST memory, results wanted in host memory.  `p` is filled as for mgp_fused_posterior, with
+ * p->nn_idx (b*k) and, if query_idx_host is given, p->query_idx (b) pointing at DEVICE staging
+ * buffers that this call fills; mean_host / var_host (nullable) receive copies of p->mean /
+ * p->var.  The batch is processed in chunks on two internal streams so that the upload of
+ * chunk c+1 and the download of chunk c-1 overlap the kernel of chunk c; the work is ordered
+ * after `stream` and joined back into it (synchronise `stream` before reading the host
+ * results).  Host buffers should be page-locked for the copies to overlap. */
+int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_idx_host,
+                             const int64_t* query_idx_host, double* mean_host,
+                             double* var_host, void* ws, size_t ws_bytes, void* stream);
+
 /* Test/bench hook: 0 = choose automatically (pipelined tile > tile > generic), 1 = always
  * the generic shared-memory kernel, 2 = the register-tile DMMA kernel where supported,
  * 3 = the software-pipelined tile kernel (error if the shape is unsupported).  Lets the

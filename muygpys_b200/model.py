@@ -26,19 +26,6 @@ from .hyperparameter import AnalyticScale, FixedScale, ScaleFn
 from .noise import HomoscedasticNoise, NoiseFn
 
 
-_SIDE_STREAMS = {}
-
-
-def _side_streams(dev: torch.device):
-    """Two long-lived copy/compute streams per device.  They are created once so that the
-    caching allocator's per-stream pools are reused from call to call (fresh streams would
-    force a cudaMalloc for every chunk)."""
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    return _SIDE_STREAMS[key]
-
-
 def _squeeze_response(mean: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
     """(b,r) -> (b,) when the caller's targets carry no response axis."""
     return mean[:, 0] if targets.dim() == 1 else mean
@@ -179,43 +166,25 @@ class MuyGPS:
             scale=self.scale() if scale is None else scale, **want)
 
     def _fused_pipelined(self, indices, nn_indices, test_features, train_features,
-                         train_targets, want_mean, want_var, chunks: int = 8):
-        """Host-resident index/feature batches: upload chunk i+1 on a side stream while
-        chunk i is in the fused kernel, so the end-to-end rate is max(PCIe, compute)."""
+                         train_targets, want_mean, want_var):
+        """Host-resident index batches: `mgp_fused_posterior_host` uploads chunk i+1 on a side
+        stream while chunk i is in the fused kernel, so the end-to-end rate is
+        max(PCIe, compute).  The chunk loop is native (csrc/pipeline.cu); a Python loop spent
+        more host time per chunk than the small first chunks take on the device."""
         x, y = fdev(train_features), fdev(train_targets)
-        dev = x.device
-        nn_h = torch.as_tensor(nn_indices)
-        b, k = nn_h.shape
-        q_h = torch.as_tensor(test_features if test_features is not None else train_features)
-        idx_h = None if indices is None else torch.as_tensor(indices)
-        r = 1 if y.dim() == 1 else y.shape[1]
-        mean = torch.empty((b, r), dtype=torch.float64, device=dev) if want_mean else None
-        var = torch.empty((b,), dtype=torch.float64, device=dev) if want_var else None
-        main = torch.cuda.current_stream()
-        side = _side_streams(dev)
-        for s in side:
-            s.wait_stream(main)
+        q_src = test_features if test_features is not None else train_features
+        q_h = torch.as_tensor(q_src)
         # the query points are small next to the indices: one upload, then gather by index
-        q_dev = q_h if q_h.is_cuda else q_h.to(dev, non_blocking=True)
-        side_ready = torch.cuda.Event()
-        side_ready.record(main)
-        bounds = [(c * b) // chunks for c in range(chunks + 1)]
-        for c in range(chunks):
-            lo, hi = bounds[c], bounds[c + 1]
-            if hi == lo:
-                continue
-            s = side[c % 2]
-            s.wait_event(side_ready)
-            with torch.cuda.stream(s):
-                nn_c = nn_h[lo:hi].to(dev, non_blocking=True)
-                idx_c = (torch.arange(lo, hi, device=dev) if idx_h is None
-                         else idx_h[lo:hi].to(dev, non_blocking=True))
-                self._fused(idx_c, nn_c, q_dev, x, y, want_mean=want_mean, want_var=want_var,
-                            out_mean=None if mean is None else mean[lo:hi],
-                            out_var=None if var is None else var[lo:hi])
-        for s in side:
-            main.wait_stream(s)
-        return {"mean": mean, "var": var}
+        q_dev = q_h if q_h.is_cuda else q_h.to(x.device, non_blocking=True)
+        deformation = self.kernel.deformation
+        ls = deformation.length_scales()
+        out = ops.fused_posterior_host(
+            x, q_dev, indices, nn_indices, y, kernel_id=self.kernel.kernel_id,
+            metric_id=deformation.metric.metric_id,
+            length_scale=ls if deformation.anisotropic else ls[0],
+            noise=self.noise.value(None), scale=self.scale(), want_mean=want_mean,
+            want_var=want_var)
+        return {"mean": out.get("mean"), "var": out.get("var")}
 
     def fused_regress(self, indices, nn_indices, test_features, train_features, train_targets,
                       want_mean=True, want_var=True):
@@ -225,7 +194,7 @@ class MuyGPS:
 
         if (is_host(nn_indices) and not is_host(train_features) and not is_host(train_targets)
                 and not self.noise.heteroscedastic and len(nn_indices) >= 16384
-                and (indices is None or test_features is not None)):
+                and (indices is None or (test_features is not None and is_host(indices)))):
             out = self._fused_pipelined(indices, nn_indices, test_features, train_features,
                                         train_targets, want_mean, want_var)
         else:

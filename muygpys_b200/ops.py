@@ -96,6 +96,7 @@ def fused_posterior(
     want_status: bool = False,
     out_mean: Optional[torch.Tensor] = None,
     out_var: Optional[torch.Tensor] = None,
+    _host: Optional[tuple] = None,
 ):
     """One launch of K1 over a batch of neighbourhoods.  Returns a dict of tensors.
 
@@ -168,8 +169,44 @@ def fused_posterior(
     ws_bytes = lib.mgp_fused_workspace_bytes(C.byref(p))
     if ws_bytes:
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    if _host is not None:  # (nn_idx, query_idx, mean, var) CPU tensors; see fused_posterior_host
+        hp = [None if h is None else C.c_void_p(h.data_ptr()) for h in _host]
+        L.check(lib.mgp_fused_posterior_host(C.byref(p), hp[0], hp[1], hp[2], hp[3], _p(ws),
+                                             ws_bytes, _stream()))
+        out["_host_buffers"] = _host  # keep them alive until the stream has been synchronised
+        return out
     L.check(lib.mgp_fused_posterior(C.byref(p), _p(ws), ws_bytes, _stream()))
     return out
+
+
+def fused_posterior_host(train_x, query_x, query_idx_host, nn_idx_host, train_y, *,
+                         mean_host: Optional[torch.Tensor] = None,
+                         var_host: Optional[torch.Tensor] = None, **kw):
+    """K1 with the neighbour (and batch) indices in HOST memory: `mgp_fused_posterior_host`
+    uploads them chunk by chunk on two internal streams under the kernels of the previous
+    chunks and, when `mean_host` / `var_host` (CPU float64 tensors, ideally pinned) are given,
+    streams the results back the same way.  Returns the device tensors like fused_posterior;
+    synchronise the current stream before reading the host outputs."""
+    train_x = as_2d(fdev(train_x, "train_features"))
+    dev = train_x.device
+
+    def host_i64(a, name):
+        t = torch.as_tensor(a)
+        if t.is_cuda:
+            raise TypeError(f"{name} must be a host array")
+        return t.to(i64).contiguous()
+
+    nn_h = host_i64(nn_idx_host, "nn_indices")
+    if nn_h.dim() != 2:
+        raise ValueError(f"nn_indices must be (batch_count, nn_count), not {tuple(nn_h.shape)}")
+    idx_h = None if query_idx_host is None else host_i64(query_idx_host, "indices")
+    for name, h in (("mean_host", mean_host), ("var_host", var_host)):
+        if h is not None and (h.is_cuda or h.dtype != f64 or not h.is_contiguous()):
+            raise TypeError(f"{name} must be a contiguous host float64 tensor")
+    nn_stage = torch.empty(nn_h.shape, dtype=i64, device=dev)
+    idx_stage = None if idx_h is None else torch.empty(idx_h.shape, dtype=i64, device=dev)
+    return fused_posterior(train_x, query_x, idx_stage, nn_stage, train_y,
+                           _host=(nn_h, idx_h, mean_host, var_host), **kw)
 
 
 def fast_mean(train_x, query_x, query_idx, nn_idx, coeff_row, coeffs, *, kernel_id, metric_id,

@@ -275,3 +275,36 @@ def test_reference_error_behaviour():
                              torch.rand(9, dtype=torch.float64, device="cuda"))
     sampled = P("log_sample", (0.01, 1.0))
     assert 0.01 <= sampled() <= 1.0
+
+
+@pytest.mark.gpu
+def test_host_buffer_pipeline_matches_single_launch():
+    """`mgp_fused_posterior_host` (indices in pinned host memory, chunked copy/compute pipeline
+    on two internal streams, results streamed back to host buffers) gives bit for bit what one
+    launch over device-resident indices gives -- with and without batch indices, for a batch
+    that is not a multiple of the chunk size."""
+    import torch
+
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(11)
+    n, b, k = 50_000, 41_237, 50
+    x = torch.as_tensor(rng.uniform(size=(n, 2))).cuda()
+    y = torch.as_tensor(rng.normal(size=(n, 1))).cuda()
+    q = torch.as_tensor(rng.uniform(size=(b, 2))).cuda()
+    nn, _ = ops.knn(x, q, k)
+    kw = dict(kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3, scale=1.3)
+    want = ops.fused_posterior(x, q, None, nn, y, **kw)
+    nn_pin = nn.cpu().pin_memory()
+    mean_pin = torch.empty((b, 1), dtype=torch.float64).pin_memory()
+    var_pin = torch.empty((b,), dtype=torch.float64).pin_memory()
+    got = ops.fused_posterior_host(x, q, None, nn_pin, y, mean_host=mean_pin, var_host=var_pin, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(got["mean"], want["mean"]) and torch.equal(got["var"], want["var"])
+    assert torch.equal(mean_pin, want["mean"].cpu()) and torch.equal(var_pin, want["var"].cpu())
+    # batch indices (a permutation of the query rows) from pageable host memory, int32 indices
+    perm = rng.permutation(b)
+    got2 = ops.fused_posterior_host(x, q[torch.as_tensor(np.argsort(perm)).cuda()], perm,
+                                    nn.cpu().numpy().astype(np.int32), y, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(got2["mean"], want["mean"]) and torch.equal(got2["var"], want["var"])
