@@ -32,14 +32,6 @@ constexpr double GRAM_FIXUP_RATIO = 1.0 / 256.0;
 #define MGP_GRAM_CHUNKS 1
 #endif
 
-// same instruction as dmma_acc() but not volatile: the Gram loop has no ordering to protect
-// and the scheduler may interleave it with the loads
-__device__ __forceinline__ void dmma_free(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-      : "+d"(c0), "+d"(c1)
-      : "d"(a), "d"(b));
-}
-
 struct GramCtx {
   const double* train_x;
   const double* qrow;       // the query point's row

@@ -23,6 +23,13 @@ __device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, doubl
       : "d"(a), "d"(b));
 }
 
+// same instruction, not volatile: the scheduler may move it across other instructions
+__device__ __forceinline__ void dmma_free(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ double rsqrt_seed(double x) {
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RSQ64H, ~20 bits
