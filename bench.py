@@ -154,15 +154,18 @@ class ClockSampler:
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []  # (arrival time, fields)
         self.proc = None
         self.index = index
+        self.t_begin = None
 
     def start(self):
+        """Launch the nvidia-smi loop (takes up to seconds to produce its first line on an
+        8-GPU box, so this is called before the warm-up)."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -170,15 +173,30 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def begin(self):
+        """The timed region starts now: only later samples count."""
+        self.t_begin = time.monotonic()
+
+    def stop(self, keep_loaded=None):
+        """Samples since begin().  If the timed region was too short for even one sample,
+        `keep_loaded()` (the same device step, untimed) is run for up to 3 s until two arrive,
+        so that the clocks are still read under this load; the JSON says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        note = "timed region"
+        if keep_loaded is not None and not [1 for t, _ in self.rows if t >= t0]:
+            note = "same load continued after a timed region shorter than the sampling period"
+            deadline = time.monotonic() + 3.0
+            while time.monotonic() < deadline and len([1 for t, _ in self.rows if t >= t0]) < 2:
+                keep_loaded()
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        self.note = note
+        for r in [f for t, f in self.rows if t >= t0]:
             try:
                 sm.append(float(r[0]))
                 smax.append(float(r[1]))
@@ -189,7 +207,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "sampled_during": self.note, "reasons": sorted(reasons)}
 
 
 def run_ours(args):
@@ -250,12 +268,13 @@ def run_ours(args):
         return ops.fused_posterior(x, q, None, nn, y, **fused_kw)
 
     # ---- device-resident timing: K steps, L2 flushed between steps ------------------
+    sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi needs a moment before its first line: start before warm-up
     for _ in range(args.warmup):
         flush.zero_()
         step_device()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.begin()
     evs = []
     for _ in range(args.steps):
         flush.zero_()
@@ -291,7 +310,12 @@ def run_ours(args):
         b.record()
         e_evs.append((a, b))
     barrier()
-    clocks = sampler.stop()
+    def keep_loaded():
+        for _ in range(20):
+            step_device()
+        torch.cuda.synchronize()
+
+    clocks = sampler.stop(keep_loaded)
     e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e_evs)], device=dev)
     # what the host link of this box gives for the same pinned index buffer (explains e2e)
     nn_stage = torch.empty_like(nn)
