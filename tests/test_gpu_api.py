@@ -308,3 +308,29 @@ def test_host_buffer_pipeline_matches_single_launch():
                                     nn.cpu().numpy().astype(np.int32), y, **kw)
     torch.cuda.synchronize()
     assert torch.equal(got2["mean"], want["mean"]) and torch.equal(got2["var"], want["var"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,k,r,d,hetero", [(100, 12, 3, 2, False), (3700, 30, 2, 5, True),
+                                            (20_000, 20, 1, 12, False)])
+def test_host_buffer_pipeline_shapes(b, k, r, d, hetero):
+    """The host-buffer entry point on batches smaller than one kernel wave, multi-response
+    targets, heteroscedastic nugget slices, every optional output, and the d > 8 kernel."""
+    import torch
+
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(b + k)
+    n = 5_000
+    x = torch.as_tensor(rng.uniform(size=(n, d))).cuda()
+    y = torch.as_tensor(rng.normal(size=(n, r))).cuda()
+    q = torch.as_tensor(rng.uniform(size=(b, d))).cuda()
+    nn, _ = ops.knn(x, q, k)
+    noise = torch.as_tensor(rng.uniform(1e-3, 1e-2, size=(b, k))).cuda() if hetero else 1e-3
+    kw = dict(kernel_id=3, metric_id=0, length_scale=0.3 * np.sqrt(d), noise=noise, scale=0.7,
+              want_yky=True, want_coeffs=True, want_status=True)
+    want = ops.fused_posterior(x, q, None, nn, y, **kw)
+    got = ops.fused_posterior_host(x, q, None, nn.cpu().numpy(), y, **kw)
+    torch.cuda.synchronize()
+    for key in ("mean", "var", "yky", "coeffs", "status"):
+        assert torch.equal(got[key], want[key]), key
