@@ -54,7 +54,47 @@ def make_data(seed, n=N_TRAIN, t=N_TEST):
     return x, y, q
 
 
-# ---- CPU reference arm (numpy restatement of the reference's numpy backend) -----------
+# ---- CPU reference arm ------------------------------------------------------------------
+# The UNMODIFIED reference (MuyGPyS, numpy backend) through its own public call
+# `MuyGPyS.examples.from_indices.regress_from_indices` when it is importable (the build
+# container installs it under baseline/_ref, which travels to the GPU box); otherwise the numpy
+# restatement of the same pipeline from oracle/.  Either way: fork-per-core over disjoint row
+# chunks, neighbours precomputed and not timed -- the same work the GPU arm times.
+_REF = {}
+
+
+def _reference_model():
+    """(MuyGPS object of the real reference, its regress_from_indices) or None."""
+    if "model" in _REF:
+        return _REF["model"]
+    root = os.path.dirname(os.path.abspath(__file__))
+    for extra in (os.path.join(root, "oracle", "ref_shims"), os.path.join(root, "baseline", "_ref")):
+        if os.path.isdir(extra) and extra not in sys.path:
+            sys.path.append(extra)
+    try:
+        from MuyGPyS.examples.from_indices import regress_from_indices as ref_regress
+        from MuyGPyS.gp import MuyGPS
+        from MuyGPyS.gp.deformation import Isotropy, l2
+        from MuyGPyS.gp.hyperparameter import Parameter
+        from MuyGPyS.gp.kernels import Matern
+        from MuyGPyS.gp.noise import HomoscedasticNoise
+
+        model = MuyGPS(kernel=Matern(smoothness=Parameter(1.5),
+                                     deformation=Isotropy(l2, length_scale=Parameter(LENGTH_SCALE))),
+                       noise=HomoscedasticNoise(NOISE))
+        _REF["model"] = (model, ref_regress)
+    except Exception:  # noqa: BLE001  (not installed, or a missing optional dependency)
+        _REF["model"] = None
+    return _REF["model"]
+
+
+def _ref_chunk(args):
+    x, y, q, nn = args
+    model, ref_regress = _REF["model"]
+    mean, var = ref_regress(model, np.arange(q.shape[0]), nn, q, x, y[:, None])
+    return float(np.ravel(mean)[0] + np.ravel(var)[0])
+
+
 def _cpu_chunk(args):
     from oracle import numpy_oracle as O
 
@@ -72,6 +112,10 @@ class CpuReference:
     def __init__(self, rows_per_core, cores, seed=2, n_train=200_000):
         import multiprocessing as mp
 
+        self.kind = "reference" if _reference_model() is not None else "port"
+        chunk_fn = _ref_chunk if self.kind == "reference" else _cpu_chunk
+        self.chunk_fn = chunk_fn
+
         from scipy.spatial import cKDTree
 
         x, y, _ = make_data(seed, n=n_train, t=1)
@@ -86,11 +130,11 @@ class CpuReference:
             uniq, inv = np.unique(nn[sl], return_inverse=True)
             self.jobs.append((x[uniq], y[uniq], q[sl], inv.reshape(nn[sl].shape)))
         self.pool = mp.get_context("fork").Pool(cores)
-        self.pool.map(_cpu_chunk, [(j[0], j[1], j[2][:4], j[3][:4]) for j in self.jobs])
+        self.pool.map(chunk_fn, [(j[0], j[1], j[2][:4], j[3][:4]) for j in self.jobs])
 
     def step(self):
         t0 = time.perf_counter()
-        self.pool.map(_cpu_chunk, self.jobs)
+        self.pool.map(self.chunk_fn, self.jobs)
         return time.perf_counter() - t0
 
     def close(self):
@@ -102,7 +146,7 @@ def cpu_reference(rows_per_core, cores, repeats=2):
     ref = CpuReference(rows_per_core, cores)
     best = min(ref.step() for _ in range(repeats))
     ref.close()
-    return ref.rows / best, ref.rows, best
+    return ref.rows / best, ref.rows, best, ref.kind
 
 
 def host_cores():
@@ -128,9 +172,11 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     rows = rows_per_core * cores
     value = rows / (ms / 1e3)
-    sample = (f"{rows} test rows per step ({rows_per_core} per core) of the C2-shaped problem, "
-              f"200k-point training subsample, neighbours precomputed (cKDTree), "
-              f"fork-per-core over disjoint row chunks")
+    impl_name = ("MuyGPyS 0.9.0 numpy backend, MuyGPyS.examples.from_indices.regress_from_indices"
+                 if ref.kind == "reference" else "numpy restatement (oracle/) of the reference")
+    sample = (f"{impl_name}: {rows} test rows per step ({rows_per_core} per core) of the "
+              f"C2-shaped problem, 200k-point training subsample, neighbours precomputed "
+              f"(cKDTree), fork-per-core over disjoint row chunks")
     print(json.dumps({
         "impl": "reference", "metric": "neighbourhoods/s (k=50 fused solve+posterior)",
         "value": value, "unit": "neighbourhoods/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -139,7 +185,7 @@ def run_reference(args):
         "config": {"workload": "C2: 2-D, 1M train / 100k test, Matern 3/2, k=50, mean+variance",
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": "neighbourhoods/s", "cores": cores,
-                         "kind": "port", "sample": sample},
+                         "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": "neighbourhoods/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }))
@@ -369,7 +415,7 @@ def run_ours(args):
             hbm_peak = 6650.0  # fallback stated in B200_PROFILING.md
         cores = host_cores()
         cpu_rows = 20000  # ~5 s per pass on one core's share
-        cpu_val, cpu_n, cpu_secs = cpu_reference(cpu_rows, cores)
+        cpu_val, cpu_n, cpu_secs, cpu_kind = cpu_reference(cpu_rows, cores)
         out = {
             "metric": "neighbourhoods/s (k=50 fused solve+posterior)",
             "value": value, "unit": "neighbourhoods/s", "n_gpus": world, "steps": args.steps,
@@ -409,8 +455,10 @@ def run_ours(args):
                         "frac": per_gpu_nbhd * BYTES_PER_NBHD / 1e9 / hbm_peak},
                 "probe": peak},
             "cpu_baseline": {
-                "value": cpu_val, "unit": "neighbourhoods/s", "cores": cores, "kind": "port",
-                "sample": f"{cpu_n} test rows of the same C2-shaped problem (200k-point "
+                "value": cpu_val, "unit": "neighbourhoods/s", "cores": cores, "kind": cpu_kind,
+                "sample": ("MuyGPyS 0.9.0 numpy backend (regress_from_indices), "
+                           if cpu_kind == "reference" else "numpy restatement (oracle/), ")
+                          + f"{cpu_n} test rows of the same C2-shaped problem (200k-point "
                           f"training subsample), fork-per-core, {cpu_secs:.1f} s"},
             "loo": {"metric": "LOO-mse objective evaluations/s (fused obj_fn, k=50)",
                     "evals_per_s": n_eval / float(loo_s),
