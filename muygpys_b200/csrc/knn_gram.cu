@@ -82,7 +82,7 @@ __device__ __forceinline__ void kg_cp_async8(void* smem_dst, const void* gmem_sr
 }
 
 // VEC: d even and both arrays 16-byte aligned -> 16-byte asynchronous copies
-template <bool VEC>
+template <bool VEC, typename IdxT>
 __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
     const double* __restrict__ train, long long n, const double* __restrict__ queries,
     long long q, int d, int kk, const int64_t* __restrict__ self_idx,
@@ -107,9 +107,11 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
   // arrays they sat in local memory, and with the L1 carved down to ~30 KB by the staging
   // buffers every shift of an insertion was an L2 round trip (ncu: 2/3 of all warp time went to
   // the insertion loop and to the other six warps waiting for it at the barrier).
-  SmemHeap top;
+  // Rows are stored as offsets into this CTA's slice of the training set: 16 bits when the
+  // slice is short enough, which is what lets two CTAs share an SM up to k = 50.
+  SmemHeapT<IdxT> top;
   top.hd = stage + 2 * BUF;
-  top.hi = reinterpret_cast<int*>(top.hd + (size_t)kk * KG_Q);
+  top.hi = reinterpret_cast<IdxT*>(top.hd + (size_t)kk * KG_Q);
   top.nt = KG_Q;
   top.t = tid;
   const bool owner = tid < KG_Q && q0 + tid < q;
@@ -237,15 +239,15 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
         const int j = __ffsll((long long)m) - 1;
         m &= m - 1;
         const double s = Ds[tid * (KG_X + 1) + j];
-        const int id = (int)(x0 + j);
-        if (id == self) continue;
+        if (x0 + j == self) continue;
+        const int id = (int)(x0 + j - x_begin);
         if (size < kk) {
           top.push(size, s, id);
           if (++size == kk) {
             worst = top.D(0);
             worst_i = top.I(0);
           }
-        } else if (SmemHeap::less(s, id, worst, worst_i)) {
+        } else if (SmemHeapT<IdxT>::less(s, id, worst, worst_i)) {
           top.replace_root(kk, s, id);
           worst = top.D(0);
           worst_i = top.I(0);
@@ -267,13 +269,13 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
     }
     if (nsplit == 1) {
       for (int i = 0; i < kk; ++i) {
-        cand_idx[(q0 + tid) * kk + i] = i < size ? top.I(i) : INT_MAX;
+        cand_idx[(q0 + tid) * kk + i] = i < size ? (long long)top.I(i) + x_begin : INT_MAX;
         cand_s[(q0 + tid) * kk + i] = i < size ? top.D(i) : DBL_MAX;
       }
     } else {
       const long long base = ((q0 + tid) * nsplit + blockIdx.y) * kk;
       for (int i = 0; i < kk; ++i) {
-        part_idx[base + i] = i < size ? top.I(i) : INT_MAX;
+        part_idx[base + i] = i < size ? (int)(top.I(i) + x_begin) : INT_MAX;
         part_s[base + i] = i < size ? top.D(i) : DBL_MAX;
       }
     }
@@ -415,6 +417,8 @@ int gram_splits(long long n, long long q) {
   if (hi > 64) hi = 64;
   if (hi < 1) hi = 1;
   long long lo = (wave + qblocks - 1) / qblocks;
+  const long long for_short_rows = (n + 65535) / 65536;  // slices that fit 16-bit row offsets
+  if (lo < for_short_rows) lo = for_short_rows;
   if (lo > hi) lo = hi;
   long long best = lo;
   double best_eff = 0.0;
@@ -496,21 +500,24 @@ int launch_knn_gram(const double* train, long long n, const double* queries, lon
   long long split_len = (n + ns - 1) / ns;
   split_len = (split_len + KG_X - 1) / KG_X * KG_X;
   const dim3 grid((unsigned)((q + KG_Q - 1) / KG_Q), (unsigned)ns);
-  const size_t kg_smem = 2 * 2 * KG_Q * KG_LD * sizeof(double) + (size_t)kk * KG_Q * 12;
   const bool vec = d % 2 == 0 && (uintptr_t)train % 16 == 0 && (uintptr_t)queries % 16 == 0;
-  if (vec) {
-    cudaFuncSetAttribute(knn_gram_filter_kernel<true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem);
-    knn_gram_filter_kernel<true><<<grid, 256, kg_smem, s>>>(
-        train, n, queries, q, d, kk, self_idx, w.xn, w.qn, split_len, ns, w.part_idx, w.part_s,
-        w.cand_idx, w.cand_s);
-  } else {
-    cudaFuncSetAttribute(knn_gram_filter_kernel<false>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem);
-    knn_gram_filter_kernel<false><<<grid, 256, kg_smem, s>>>(
-        train, n, queries, q, d, kk, self_idx, w.xn, w.qn, split_len, ns, w.part_idx, w.part_s,
-        w.cand_idx, w.cand_s);
-  }
+  // 16-bit in-slice rows (10 instead of 12 bytes per heap entry) whenever a slice is short enough
+  const bool short_rows = split_len <= 65536;
+  const size_t kg_smem =
+      2 * 2 * KG_Q * KG_LD * sizeof(double) + (size_t)kk * KG_Q * (short_rows ? 10 : 12);
+#define MGP_KG_LAUNCH(VEC_, IDX_)                                                              \
+  do {                                                                                         \
+    cudaFuncSetAttribute(knn_gram_filter_kernel<VEC_, IDX_>,                                   \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem);           \
+    knn_gram_filter_kernel<VEC_, IDX_><<<grid, 256, kg_smem, s>>>(                             \
+        train, n, queries, q, d, kk, self_idx, w.xn, w.qn, split_len, ns, w.part_idx,          \
+        w.part_s, w.cand_idx, w.cand_s);                                                       \
+  } while (0)
+  if (vec && short_rows) MGP_KG_LAUNCH(true, unsigned short);
+  else if (vec) MGP_KG_LAUNCH(true, int);
+  else if (short_rows) MGP_KG_LAUNCH(false, unsigned short);
+  else MGP_KG_LAUNCH(false, int);
+#undef MGP_KG_LAUNCH
   if (ns > 1) {
     if (kk <= 48)
       knn_gram_merge_kernel<48><<<(unsigned)((q + 127) / 128), 128, 0, s>>>(

@@ -8,12 +8,14 @@ namespace mgp {
 // but always in different banks).  Per-thread arrays in local memory spilled to L2 -- 1.5 MB of
 // lists per SM -- and every shift of the sorted insertion was an L2 round trip; the heap needs
 // log2(k) shared-memory steps per accepted candidate.  The root is the current worst entry.
-struct SmemHeap {
+// IdxT is the stored row type (int, or unsigned short for in-slice offsets below 65536).
+template <typename IdxT>
+struct SmemHeapT {
   double* hd;
-  int* hi;
+  IdxT* hi;
   int nt, t;
   __device__ __forceinline__ double& D(int i) { return hd[i * nt + t]; }
-  __device__ __forceinline__ int& I(int i) { return hi[i * nt + t]; }
+  __device__ __forceinline__ IdxT& I(int i) { return hi[i * nt + t]; }
   static __device__ __forceinline__ bool less(double da, int ia, double db, int ib) {
     return da < db || (da == db && ia < ib);
   }
@@ -26,11 +28,11 @@ struct SmemHeap {
       const int ip = I(p);
       if (!less(dp, ip, s, id)) break;
       D(i) = dp;
-      I(i) = ip;
+      I(i) = (IdxT)ip;
       i = p;
     }
     D(i) = s;
-    I(i) = id;
+    I(i) = (IdxT)id;
   }
   // replace the root of a heap of `size` entries by (s, id) and restore the heap
   __device__ __forceinline__ void replace_root(int size, double s, int id) {
@@ -51,12 +53,14 @@ struct SmemHeap {
       }
       if (!less(s, id, dc, ic)) break;
       D(i) = dc;
-      I(i) = ic;
+      I(i) = (IdxT)ic;
       i = c;
     }
     D(i) = s;
-    I(i) = id;
+    I(i) = (IdxT)id;
   }
 };
+
+using SmemHeap = SmemHeapT<int>;
 
 }  // namespace mgp
