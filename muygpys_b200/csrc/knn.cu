@@ -174,8 +174,9 @@ static int launch_knn(const double* train, long long n, const double* queries, l
 using namespace mgp;
 
 extern "C" size_t mgp_knn_workspace_bytes(int64_t n, int64_t q, int32_t d, int32_t k) {
-  if (d <= 8 || n < 1 || q < 8 || k < 1) return 0;
+  if (n < 1 || q < 8 || k < 1) return 0;
   if (mgp::knn_gram_supported(n, q, d, k)) return mgp::knn_gram_workspace_bytes(n, q, k);
+  if (d <= 8) return 0;
   return mgp::knn_tiled_workspace_bytes(n, q, k);
 }
 
@@ -196,14 +197,12 @@ extern "C" int mgp_knn(const double* train, int64_t n, const double* queries, in
   MGP_REQUIRE(!exclude_self || self_idx, MGP_ERR_BAD_ARG, "exclude_self needs self_idx");
   const int64_t* self = exclude_self ? self_idx : nullptr;
   cudaStream_t s = (cudaStream_t)stream;
-  if (d > 8 && q >= 8) {
-    // DMMA pre-filter + certified exact re-rank where it pays, else the register-tiled exact
-    // sweep; a handful of queries take the warp kernel
-    if (knn_gram_supported(n, q, d, k))
-      return launch_knn_gram(train, n, queries, q, d, k, self, out_idx, out_d2, ws, ws_bytes, s);
+  // DMMA pre-filter + certified exact re-rank where it pays
+  if (q >= 8 && knn_gram_supported(n, q, d, k))
+    return launch_knn_gram(train, n, queries, q, d, k, self, out_idx, out_d2, ws, ws_bytes, s);
+  if (d > 8 && q >= 8)  // register-tiled exact sweep; a handful of queries take the warp kernel
     return launch_knn_tiled(train, n, queries, q, d, k, self, out_idx, out_d2, ws, ws_bytes, s,
                             nullptr, nullptr);
-  }
   if (k <= 64) return launch_knn<64>(train, n, queries, q, d, k, self, out_idx, out_d2, s);
   if (k <= 128) return launch_knn<128>(train, n, queries, q, d, k, self, out_idx, out_d2, s);
   return launch_knn<256>(train, n, queries, q, d, k, self, out_idx, out_d2, s);

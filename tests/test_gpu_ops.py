@@ -448,9 +448,10 @@ def test_high_dimensional_gram_cancellation_fixup(kid):
 
 @pytest.mark.parametrize("layout,d", [("random", 33), ("offset", 33), ("duplicates", 33),
                                       ("lattice", 33), ("random", 12), ("lattice", 9),
-                                      ("duplicates", 16)])
+                                      ("duplicates", 16), ("random", 4), ("lattice", 5),
+                                      ("duplicates", 8), ("offset", 2)])
 def test_high_d_knn_gram_prefilter_is_exact(layout, d):
-    """d > 8: the DMMA Gram pre-filter + certified exact re-rank (csrc/knn_gram.cu) must return
+    """Any d (n >= 2048): the DMMA Gram pre-filter + certified exact re-rank (csrc/knn_gram.cu) must return
     bit for bit what the exact sweep returns -- on random data, on data far from the origin
     (large norms -> large cancellation bound), with every point repeated 12 times (ties straddle
     the candidate boundary: certification fails and the exact sweep re-runs those queries) and
