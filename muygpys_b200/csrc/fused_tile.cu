@@ -22,8 +22,8 @@
 // layout in shared memory, from where each tile column is picked up with one
 // LDS.128 per lane per tile.
 //
-// Supported shapes: roundup8(roundup4(k) + 1 + r) <= 104 (T <= 7 tile rows with the factor in
-// registers, T <= 13 with the factor in shared memory), k <= 127.  d <= 8 assembles from staged
+// Supported shapes: roundup8(roundup4(k) + 1 + r) <= 128 (T <= 7 tile rows with the factor in
+// registers, T <= 16 with the factor in shared memory), k <= 127.  d <= 8 assembles from staged
 // coordinates; d > 8 takes its distances from DMMA Gram tiles (gram.cuh, instantiated in
 // fused_tile_gram.cu).  Everything else takes the generic shared-memory kernel.  The kernel
 // template itself is in fused_tile_kernel.cuh.
@@ -37,15 +37,15 @@ static int g_variant = 0;  // 0 auto (pipe > tile > generic), 1 generic, 2 tile,
 int fused_variant() { return g_variant; }
 
 // d > 8 instantiations live in fused_tile_gram.cu
-int launch_fused_tile_gram(const mgp_problem* p, const Model& model, int T, long long blocks,
-                           int warps, size_t smem, size_t warp_doubles, cudaStream_t stream);
+int launch_fused_tile_gram(const mgp_problem* p, const Model& model, int T,
+                           size_t shared_doubles, size_t warp_doubles, cudaStream_t stream);
 
 int fused_tile_supported(const mgp_problem* p, const Model& model) {
   (void)model;
   if (g_variant == 1) return 0;
   if (p->d > TILE_MAX_D && g_gram_off) return 0;
   if (p->k > 127) return 0;  // the row prefetch stages at most 128 points per warp
-  return tiles_needed(p->k, p->r) <= 13;
+  return tiles_needed(p->k, p->r) <= 16;
 }
 
 int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t ws_bytes,
@@ -63,19 +63,8 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
                               2 * (size_t)(((p->k * p->r) + 1) & ~1);
   const size_t shared_doubles =
       (size_t)((((a.n_elem + 2) / 2) + 1) & ~1) + MGP_MAX_ANISO_DIM;
-  const bool smem_l = T > 7;
-  int warps = TILE_WARPS;
-  while (warps > 1 &&
-         (shared_doubles + warp_doubles * warps) * sizeof(double) > (size_t)max_smem_optin())
-    --warps;  // large k: fewer neighbourhoods in flight per CTA
-  const size_t smem = (shared_doubles + warp_doubles * warps) * sizeof(double);
-  MGP_REQUIRE(smem <= (size_t)max_smem_optin(), MGP_ERR_UNSUPPORTED,
-              "tile kernel shared memory %zu too large", smem);
-  long long blocks = (p->b + warps - 1) / warps;
-  const long long cap = (long long)sm_count() * (smem_l ? 1 : 3);
-  if (blocks > cap) blocks = cap;
-  if (a.gram) return launch_fused_tile_gram(p, model, T, blocks, warps, smem, warp_doubles, stream);
-  return launch_tile_instance<false>(a, T, smem_l, blocks, warps, smem, warp_doubles, stream);
+  if (a.gram) return launch_fused_tile_gram(p, model, T, shared_doubles, warp_doubles, stream);
+  return launch_tile_instance<false>(a, T, p->b, shared_doubles, warp_doubles, stream);
 }
 
 }  // namespace mgp

@@ -5,15 +5,15 @@
 
 namespace mgp {
 
-int launch_fused_tile_gram(const mgp_problem* p, const Model& model, int T, long long blocks,
-                           int warps, size_t smem, size_t warp_doubles, cudaStream_t stream) {
+int launch_fused_tile_gram(const mgp_problem* p, const Model& model, int T,
+                           size_t shared_doubles, size_t warp_doubles, cudaStream_t stream) {
   TileArgs a;  // filled here again: the exp table of THIS translation unit must be uploaded
   const int rc = fill_tile_args(p, model, a);
   if (rc != MGP_OK) return rc;
   // one LDG.128 per lane per row needs even d and 16-byte aligned arrays
   if (p->d % 2 == 0 && ((uintptr_t)p->train_x % 16 == 0) && ((uintptr_t)p->query_x % 16 == 0))
     a.gram = 2;
-  return launch_tile_instance<true>(a, T, T > 7, blocks, warps, smem, warp_doubles, stream);
+  return launch_tile_instance<true>(a, T, p->b, shared_doubles, warp_doubles, stream);
 }
 
 }  // namespace mgp

@@ -77,7 +77,7 @@ __device__ __forceinline__ void assemble_any(int formula, double* tiles, const d
 // SMEM_L = false: finished tiles live in registers (T <= 7, three CTAs per SM).
 // SMEM_L = true : finished tiles are written back over their own cells of the shared-memory
 //                 image and re-read as DMMA fragments (one LDS.128 per tile per use), which
-//                 takes T up to 13 (k ~ 100, BASELINE config C4) at one CTA per SM.
+//                 takes T up to 16 (k <= 124; k ~ 100 is BASELINE config C4).
 template <int T, bool SMEM_L, bool GRAM>
 __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
     fused_tile_kernel(const TileArgs a, size_t warp_doubles) {
@@ -385,17 +385,41 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
 namespace {
 
 // Launch the instantiation for T tile rows; GRAM selects the d > 8 assembly (gram.cuh).
+// Persistent grid: warps per CTA (<= TILE_WARPS) and CTAs per SM are chosen to maximise the
+// neighbourhoods in flight per SM under the register and shared-memory limits -- e.g. the
+// shared-memory-factor variants fit 2 x 4 warps up to T = 9 and 2 x 3 warps at T = 10.
 template <bool GRAM>
-int launch_tile_instance(const TileArgs& a, int T, bool smem_l, long long blocks, int warps,
-                         size_t smem, size_t warp_doubles, cudaStream_t stream) {
-  (void)smem_l;
+int launch_tile_instance(const TileArgs& a, int T, long long rows, size_t shared_doubles,
+                         size_t warp_doubles, cudaStream_t stream) {
+  const size_t smem_max = (size_t)max_smem_optin();
 #define MGP_TILE(TT, SL)                                                                      \
-  case TT:                                                                                    \
+  case TT: {                                                                                  \
     cudaFuncSetAttribute(fused_tile_kernel<TT, SL, GRAM>,                                     \
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-    fused_tile_kernel<TT, SL, GRAM><<<(unsigned)blocks, warps * 32, smem, stream>>>(          \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);         \
+    int best_w = 0, best_per_sm = 0;                                                          \
+    for (int w = TILE_WARPS; w >= 1; --w) {                                                   \
+      const size_t smem_w = (shared_doubles + warp_doubles * w) * sizeof(double);             \
+      if (smem_w > smem_max) continue;                                                        \
+      int per_sm = 0;                                                                         \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                      \
+              &per_sm, fused_tile_kernel<TT, SL, GRAM>, w * 32, smem_w) != cudaSuccess)       \
+        per_sm = 0;                                                                           \
+      if (w * per_sm > best_w * best_per_sm) {                                                \
+        best_w = w;                                                                           \
+        best_per_sm = per_sm;                                                                 \
+      }                                                                                       \
+    }                                                                                         \
+    MGP_REQUIRE(best_w > 0, MGP_ERR_UNSUPPORTED,                                              \
+                "tile kernel: no launch configuration fits (T=%d, %zu doubles per warp)", T,  \
+                warp_doubles);                                                                \
+    const size_t smem = (shared_doubles + warp_doubles * best_w) * sizeof(double);            \
+    long long blocks = (rows + best_w - 1) / best_w;                                          \
+    const long long cap = (long long)sm_count() * best_per_sm;                                \
+    if (blocks > cap) blocks = cap;                                                           \
+    fused_tile_kernel<TT, SL, GRAM><<<(unsigned)blocks, best_w * 32, smem, stream>>>(         \
         a, warp_doubles);                                                                     \
-    break;
+    break;                                                                                    \
+  }
   switch (T) {
     MGP_TILE(1, false)
     MGP_TILE(2, false)
@@ -410,6 +434,9 @@ int launch_tile_instance(const TileArgs& a, int T, bool smem_l, long long blocks
     MGP_TILE(11, true)
     MGP_TILE(12, true)
     MGP_TILE(13, true)
+    MGP_TILE(14, true)
+    MGP_TILE(15, true)
+    MGP_TILE(16, true)
     default:
       set_error("tile variant does not support %d tile rows", T);
       return MGP_ERR_UNSUPPORTED;

@@ -332,7 +332,8 @@ def test_high_d_knn_tiled_matches_warp_kernel_and_oracle():
 
 SHAPES = [(1, 1, 2), (2, 1, 1), (3, 2, 2), (7, 1, 3), (8, 3, 2), (12, 5, 2), (30, 10, 3),
           (33, 1, 2), (49, 1, 2), (50, 10, 2), (51, 1, 2), (52, 1, 2), (60, 4, 5), (64, 1, 8),
-          (99, 2, 2), (100, 1, 2), (100, 3, 2), (101, 1, 2), (104, 1, 2), (120, 1, 2)]
+          (99, 2, 2), (100, 1, 2), (100, 3, 2), (101, 1, 2), (104, 1, 2), (108, 2, 2),
+          (120, 1, 2), (124, 1, 2), (125, 1, 2)]
 
 
 @pytest.mark.parametrize("k,r,d", SHAPES, ids=lambda v: str(v))
