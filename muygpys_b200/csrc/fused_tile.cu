@@ -36,9 +36,13 @@ static int g_variant = 0;  // 0 auto (pipe > tile > generic), 1 generic, 2 tile,
 
 int fused_variant() { return g_variant; }
 
-// d > 8 instantiations live in fused_tile_gram.cu
+// the other instantiations: d > 8 in fused_tile_gram*.cu, T > TILE_T_SPLIT in fused_tile*_big.cu
 int launch_fused_tile_gram(const mgp_problem* p, const Model& model, int T,
                            size_t shared_doubles, size_t warp_doubles, cudaStream_t stream);
+int launch_fused_tile_gram_big(const mgp_problem* p, const Model& model, int T,
+                               size_t shared_doubles, size_t warp_doubles, cudaStream_t stream);
+int launch_fused_tile_big(const mgp_problem* p, const Model& model, int T,
+                          size_t shared_doubles, size_t warp_doubles, cudaStream_t stream);
 
 int fused_tile_supported(const mgp_problem* p, const Model& model) {
   (void)model;
@@ -63,8 +67,14 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
                               2 * (size_t)(((p->k * p->r) + 1) & ~1);
   const size_t shared_doubles =
       (size_t)((((a.n_elem + 2) / 2) + 1) & ~1) + MGP_MAX_ANISO_DIM;
-  if (a.gram) return launch_fused_tile_gram(p, model, T, shared_doubles, warp_doubles, stream);
-  return launch_tile_instance<false>(a, T, p->b, shared_doubles, warp_doubles, stream);
+  if (a.gram)
+    return T <= TILE_T_SPLIT
+               ? launch_fused_tile_gram(p, model, T, shared_doubles, warp_doubles, stream)
+               : launch_fused_tile_gram_big(p, model, T, shared_doubles, warp_doubles, stream);
+  if (T > TILE_T_SPLIT)
+    return launch_fused_tile_big(p, model, T, shared_doubles, warp_doubles, stream);
+  return launch_tile_instance<false, 1, TILE_T_SPLIT>(a, T, p->b, shared_doubles, warp_doubles,
+                                                      stream);
 }
 
 }  // namespace mgp

@@ -388,12 +388,17 @@ namespace {
 // Persistent grid: warps per CTA (<= TILE_WARPS) and CTAs per SM are chosen to maximise the
 // neighbourhoods in flight per SM under the register and shared-memory limits -- e.g. the
 // shared-memory-factor variants fit 2 x 4 warps up to T = 9 and 2 x 3 warps at T = 10.
-template <bool GRAM>
+// Only the instantiations with TLO <= T <= THI are compiled into the calling translation unit
+// (the large-T ones take tens of seconds each; four units build in parallel).
+constexpr int TILE_T_SPLIT = 10;  // fused_tile*.cu: T <= 10, fused_tile*_big.cu: T >= 11
+
+template <bool GRAM, int TLO, int THI>
 int launch_tile_instance(const TileArgs& a, int T, long long rows, size_t shared_doubles,
                          size_t warp_doubles, cudaStream_t stream) {
   const size_t smem_max = (size_t)max_smem_optin();
 #define MGP_TILE(TT, SL)                                                                      \
-  case TT: {                                                                                  \
+  case TT:                                                                                    \
+    if constexpr (TT >= TLO && TT <= THI) {                                                   \
     cudaFuncSetAttribute(fused_tile_kernel<TT, SL, GRAM>,                                     \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);         \
     int best_w = 0, best_per_sm = 0;                                                          \
@@ -419,7 +424,10 @@ int launch_tile_instance(const TileArgs& a, int T, long long rows, size_t shared
     fused_tile_kernel<TT, SL, GRAM><<<(unsigned)blocks, best_w * 32, smem, stream>>>(         \
         a, warp_doubles);                                                                     \
     break;                                                                                    \
-  }
+    } else {                                                                                  \
+      set_error("tile variant: T=%d is not compiled into this translation unit", T);          \
+      return MGP_ERR_UNSUPPORTED;                                                             \
+    }
   switch (T) {
     MGP_TILE(1, false)
     MGP_TILE(2, false)
