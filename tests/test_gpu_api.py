@@ -334,3 +334,27 @@ def test_host_buffer_pipeline_shapes(b, k, r, d, hetero):
     torch.cuda.synchronize()
     for key in ("mean", "var", "yky", "coeffs", "status"):
         assert torch.equal(got[key], want[key]), key
+
+
+@pytest.mark.gpu
+def test_host_buffer_pipeline_error_behaviour():
+    """The host-buffer entry point rejects device index arrays and mismatched shapes loudly."""
+    import torch
+
+    from muygpys_b200 import ops
+
+    x = torch.rand((100, 2), dtype=torch.float64, device="cuda")
+    y = torch.rand((100, 1), dtype=torch.float64, device="cuda")
+    q = torch.rand((8, 2), dtype=torch.float64, device="cuda")
+    nn = torch.randint(0, 100, (8, 5))
+    kw = dict(kernel_id=2, metric_id=0, length_scale=0.3, noise=1e-3)
+    with pytest.raises(TypeError):
+        ops.fused_posterior_host(x, q, None, nn.cuda(), y, **kw)
+    with pytest.raises(ValueError):
+        ops.fused_posterior_host(x, q, None, nn[:, 0], y, **kw)
+    with pytest.raises(TypeError):
+        ops.fused_posterior_host(x, q, None, nn, y, mean_host=torch.empty((8, 1)), **kw)
+    out = ops.fused_posterior_host(x, q, None, nn, y, **kw)  # tiny batch: a single chunk
+    torch.cuda.synchronize()
+    want = ops.fused_posterior(x, q, None, nn.cuda(), y, **kw)
+    assert torch.equal(out["mean"], want["mean"]) and torch.equal(out["var"], want["var"])

@@ -475,7 +475,7 @@ def test_high_d_knn_gram_prefilter_is_exact(layout, d):
         x = rng.integers(0, 2, size=(n, d)).astype(np.float64)
         qs = rng.integers(0, 2, size=(q, d)).astype(np.float64)
     xd, qd = dev(x), dev(qs)
-    for kk in (k, 88):
+    for kk in (k, 88, 100):  # 100 > 88: beyond the candidate lists, i.e. the exact sweep
         gi, gd = ops.knn(xd, qd, kk)
         want_i, want_d = O.knn_exact(x, qs, kk, chunk=16)
         np.testing.assert_array_equal(gi.cpu().numpy(), want_i)
@@ -490,3 +490,40 @@ def test_high_d_knn_gram_prefilter_is_exact(layout, d):
     order = np.argsort(dist, axis=1, kind="stable")[:, :k]
     np.testing.assert_array_equal(si.cpu().numpy(), order)
     np.testing.assert_array_equal(sd.cpu().numpy(), np.take_along_axis(dist, order, axis=1))
+
+
+@pytest.mark.parametrize("d", [12, 40])
+def test_high_dimensional_gram_training_batch_heteroscedastic(d):
+    """d > 8 with everything a training batch uses: queries taken from the training set through
+    `query_idx` (the query row is then a training row, the neighbourhood excludes it), a
+    heteroscedastic nugget tensor and the y^T K^-1 y output -- against the generic kernel and
+    the oracle."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(9000 + d)
+    n, b, k, r = 2_500, 57, 22, 2
+    x = rng.normal(size=(n, d))
+    y = rng.normal(size=(n, r))
+    bi = rng.choice(n, b, replace=False)
+    nn, _ = ops.knn(dev(x), dev(x[bi]), k, self_idx=dev(bi))
+    nn_h = nn.cpu().numpy()
+    assert not (nn_h == bi[:, None]).any()
+    noise = rng.uniform(1e-3, 5e-2, size=(b, k))
+    ls = 0.8 * np.sqrt(d)
+    kw = dict(kernel_id=O.KERNEL_MATERN_25, metric_id=O.METRIC_L2, length_scale=ls,
+              noise=dev(noise), scale=1.0, want_yky=True, want_status=True)
+    outs = {}
+    for name, variant in (("auto", 0), ("generic", 1)):
+        ops.set_fused_variant(variant)
+        outs[name] = ops.fused_posterior(dev(x), dev(x), dev(bi), nn, dev(y), **kw)
+    ops.set_fused_variant(0)
+    Kin, Kcross = O.kernel_tensors(O.KERNEL_MATERN_25, O.METRIC_L2, ls, x, x, bi, nn_h)
+    pK = O.heteroscedastic_perturb(Kin, noise)
+    want_mean = O.posterior_mean(pK, Kcross, y[nn_h])
+    want_var = O.diagonal_variance(pK, Kcross)
+    want_yky = np.einsum("bkr,bkr->b", y[nn_h], np.linalg.solve(pK, y[nn_h]))
+    for name, out in outs.items():
+        assert int(out["status"].sum()) == 0
+        assert_close(out["mean"].cpu().numpy(), want_mean, RTOL, f"{name} mean d={d}")
+        assert_close(out["var"].cpu().numpy(), want_var, RTOL, f"{name} var d={d}")
+        assert_close(out["yky"].cpu().numpy(), want_yky, RTOL, f"{name} yky d={d}")
