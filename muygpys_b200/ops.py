@@ -18,7 +18,14 @@ f64 = torch.float64
 i64 = torch.int64
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """Handle of torch's current CUDA stream (the raw getter is ~10x cheaper than building a
+    torch.cuda.Stream object, which matters for 10 k-row objective evaluations)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
