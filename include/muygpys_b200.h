@@ -159,7 +159,13 @@ int mgp_loss_partials(int32_t loss_id, const double* pred, const double* targets
 /* ---- exact KNN (a1): NN_Wrapper._get_nns          S/neighbors.py:213-262
  * out_idx (q,k) int64 ascending by distance, out_d2 (q,k) SQUARED l2.
  * exclude_self != 0 drops, for query row i, the train row self_idx[i]
- * (get_batch_nns semantics, S/neighbors.py:169-211). */
+ * (get_batch_nns semantics, S/neighbors.py:169-211).
+ * The result is that of a brute-force sweep with separately rounded subtract / multiply / add in
+ * feature order (ties to the lower train row), whichever kernel computes it: for n >= 2048,
+ * q >= 8, k <= 88 an FP64 tensor-core pre-filter proposes k + 8 candidates per query, they are
+ * re-ranked with the exact arithmetic and the answer is certified against a rounding bound;
+ * queries that cannot be certified are re-run through the exact sweep inside the same call.
+ * `ws` must hold mgp_knn_workspace_bytes(n, q, d, k) bytes. */
 size_t mgp_knn_workspace_bytes(int64_t n, int64_t q, int32_t d, int32_t k);
 int mgp_knn(const double* train, int64_t n, const double* queries, int64_t q, int32_t d,
             int32_t k, int32_t exclude_self, const int64_t* self_idx, int64_t* out_idx,
