@@ -260,11 +260,12 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
             }
           } else {
             const double b0 = l0[J][P] * dinv0[P], b1 = l1[J][P] * dinv1[P];
+            // even slices of every tile, then the odd ones: no back-to-back DMMAs on one
+            // accumulator (the register variant has the operands at hand, so this is free)
 #pragma unroll
-            for (int I = J; I < T; ++I) {
-              dmma_acc(c[I][0], c[I][1], l0[I][P], b0);
-              dmma_acc(c[I][0], c[I][1], l1[I][P], b1);
-            }
+            for (int I = J; I < T; ++I) dmma_acc(c[I][0], c[I][1], l0[I][P], b0);
+#pragma unroll
+            for (int I = J; I < T; ++I) dmma_acc(c[I][0], c[I][1], l1[I][P], b1);
           }
         }
       }
