@@ -302,7 +302,7 @@ class KnnGrid:
     Built once per training set: cell ids from the CUDA kernel, a device radix sort
     (torch.sort, plumbing) to bucket the points, and the per-cell offsets."""
 
-    POINTS_PER_CELL = 12.0
+    POINTS_PER_CELL = 6.0  # measured: 4-8 is best for k = 10..100 (tools/sweep_grid_density.py)
     MAX_CELLS = 1 << 27
 
     def __init__(self, train: torch.Tensor):
