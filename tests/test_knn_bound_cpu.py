@@ -35,3 +35,33 @@ def test_gram_identity_error_is_inside_the_certificate_margin(d, offset):
     assert err.max() <= 0.25 * margin.min()
     if offset == 0.0:
         assert margin.max() < 1e-9 * np.median(s_exact)
+
+
+@pytest.mark.parametrize("d", [12, 784])
+def test_centred_gram_distances_keep_eleven_digits_above_the_fixup_ratio(d):
+    """The d > 8 assembly of the fused kernel (csrc/gram.cuh) takes |u_i - u_j|^2 from Gram
+    tiles of the query-centred rows and recomputes by direct differences every pair with
+    |u_i - u_j|^2 < (|u_i|^2 + |u_j|^2) / 256.  Above that ratio the identity must be good to
+    ~1e-11 relative (the fused outputs are compared at 1e-10): checked here in float64 on
+    neighbourhoods far from the origin, where the uncentred identity would lose everything."""
+    rng = np.random.default_rng(d)
+    k = 40
+    centre = rng.normal(size=d) * 1e3
+    x = centre + rng.normal(size=(k, d))          # a neighbourhood of radius ~sqrt(d)
+    x[1] = x[0] + 0.05 * rng.normal(size=d)       # a close pair, still above the ratio
+    q = centre + 0.3 * rng.normal(size=d)
+    u = x - q
+    g = u @ u.T
+    n = np.diag(g)
+    s_gram = n[:, None] + n[None, :] - 2.0 * g
+    s_exact = brute_force_sq(x, x)
+    iu = np.triu_indices(k, 1)
+    keep = s_gram[iu] >= (n[:, None] + n[None, :])[iu] / 256.0
+    assert keep.sum() > 0.9 * keep.size
+    rel = np.abs(s_gram[iu] - s_exact[iu])[keep] / s_exact[iu][keep]
+    assert rel.max() < 2e-11
+    # without centring the same identity is useless at this offset
+    g0 = x @ x.T
+    n0 = np.diag(g0)
+    rel0 = np.abs((n0[:, None] + n0[None, :] - 2.0 * g0)[iu] - s_exact[iu]) / s_exact[iu]
+    assert rel0.max() > 1e-9
