@@ -9,6 +9,7 @@
 // first chunk: the only transfer that is not hidden is the first upload, and a chunk may grow
 // by about kernel time / copy time per step without stalling the pipeline.  Everything is
 // ordered after the work already queued on `stream` and joined back into it.
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -50,12 +51,15 @@ int side_streams(SideStreams** out) {
 
 // chunk boundaries: multiples of `wave` rows, sizes 2, 2, 3, 5, 7, 10, ... waves (x1.4)
 std::vector<long long> chunk_bounds(long long b, long long wave) {
+  // dev switches for tuning the schedule
+  static const double first = getenv("MGP_PIPE_FIRST") ? atof(getenv("MGP_PIPE_FIRST")) : 2.0;
+  static const double growth = getenv("MGP_PIPE_GROWTH") ? atof(getenv("MGP_PIPE_GROWTH")) : 1.4;
   std::vector<long long> bounds{0};
-  double w = 2.0;
+  double w = first;
   while (bounds.back() < b) {
     const long long sz = (long long)w < 1 ? 1 : (long long)w;
     bounds.push_back(bounds.back() + sz * wave);
-    w *= 1.4;
+    w *= growth;
   }
   bounds.back() = b;
   const size_t m = bounds.size();
