@@ -24,26 +24,27 @@ int check_launch(const char* what) {
   return MGP_OK;
 }
 
-int sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
+// Device attributes are cached PER DEVICE (a process may drive several GPUs).
+static int cached_attr(cudaDeviceAttr attr, int (&cache)[64], int fallback) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cache[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, attr, dev);
+    cache[dev] = v > 0 ? v : fallback;
   }
-  return cached;
+  return cache[dev];
+}
+
+int sm_count() {
+  static int cache[64];
+  return cached_attr(cudaDevAttrMultiProcessorCount, cache, 148);
 }
 
 int max_smem_optin() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (cached <= 0) cached = 227 * 1024;
-  }
-  return cached;
+  static int cache[64];
+  return cached_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, cache, 227 * 1024);
 }
 
 int make_model(int kernel_id, int metric_id, int d, int length_scale_count,

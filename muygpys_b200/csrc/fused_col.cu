@@ -1,0 +1,103 @@
+// Dispatch of the column-direct fused kernel (fused_col.cuh; one translation unit per covariance
+// formula: fused_col_m05.cu, _m15.cu, _m25.cu, _gauss.cu) and the one-launch leave-one-out
+// objective entry point mgp_fused_loo.
+#include "fused_col.cuh"
+
+namespace mgp {
+
+int launch_fused_col_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_col_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_col_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_col_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+
+int fused_variant();
+int validate_problem(const mgp_problem* p);
+
+static int col_formula(const Model& model) {
+  if (model.metric_id == MGP_METRIC_L2) {
+    switch (model.kernel_id) {
+      case MGP_KERNEL_MATERN_05: return F_M05;
+      case MGP_KERNEL_MATERN_15: return F_M15;
+      case MGP_KERNEL_MATERN_25: return F_M25;
+      case MGP_KERNEL_MATERN_INF: return F_GAUSS;
+      default: return -1;  // RBF handed l2 distances (reference quirk): tile kernel
+    }
+  }
+  return model.kernel_id == MGP_KERNEL_RBF ? F_GAUSS : -1;
+}
+
+int fused_col_supported(const mgp_problem* p, const Model& model) {
+  if (p->r != 1 || p->d > 3 || p->noise_bk || p->coeffs || !p->train_y) return 0;
+  const int T = col_tiles(p->k);
+  if (T < 2 || T > COL_MAX_T) return 0;
+  if (col_formula(model) < 0) return 0;
+  // 2-D points are fetched with one 16-byte cp.async each
+  if (p->d == 2 && ((((uintptr_t)p->train_x) | ((uintptr_t)p->query_x)) & 15)) return 0;
+  return 1;
+}
+
+static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& loo, int* grid_out,
+                      cudaStream_t stream) {
+  switch (col_formula(model)) {
+    case F_M05: return launch_fused_col_f0(p, model, loo, grid_out, stream);
+    case F_M15: return launch_fused_col_f1(p, model, loo, grid_out, stream);
+    case F_M25: return launch_fused_col_f2(p, model, loo, grid_out, stream);
+    case F_GAUSS: return launch_fused_col_f3(p, model, loo, grid_out, stream);
+    default:
+      set_error("column kernel does not support this kernel / metric pair");
+      return MGP_ERR_UNSUPPORTED;
+  }
+}
+
+int launch_fused_col(const mgp_problem* p, const Model& model, cudaStream_t stream) {
+  ColLoo loo = {};
+  return launch_col(p, model, loo, nullptr, stream);
+}
+
+// workspace of mgp_fused_loo: [counter (256 B)] [per-warp records] -- the record area is sized for
+// the largest grid any device of this process can run (4 CTAs per SM)
+static size_t loo_ws_bytes() {
+  return 256 + (size_t)sm_count() * 4 * COL_WARPS * MGP_PARTIALS * sizeof(double);
+}
+
+}  // namespace mgp
+
+extern "C" size_t mgp_fused_loo_workspace_bytes(const mgp_problem* p) {
+  (void)p;
+  return mgp::loo_ws_bytes();
+}
+
+extern "C" int mgp_fused_loo(const mgp_problem* p, int32_t loss_id, double boundary_scale,
+                             double* partials, void* ws, size_t ws_bytes, void* stream) {
+  using namespace mgp;
+  int rc = validate_problem(p);
+  if (rc != MGP_OK) return rc;
+  MGP_REQUIRE(partials != nullptr, MGP_ERR_BAD_ARG, "partials is required");
+  MGP_REQUIRE(loss_id == MGP_LOSS_NONE || loss_id == MGP_LOSS_MSE || loss_id == MGP_LOSS_LOOL ||
+                  loss_id == MGP_LOSS_PSEUDO_HUBER,
+              MGP_ERR_UNSUPPORTED,
+              "mgp_fused_loo finishes mse, lool and pseudo-Huber in one launch (loss_id %d needs "
+              "the two-pass path)", loss_id);
+  Model model;
+  rc = make_model(p->kernel_id, p->metric_id, p->d, p->length_scale_count, p->length_scale,
+                  &model);
+  if (rc != MGP_OK) return rc;
+  MGP_REQUIRE(fused_col_supported(p, model), MGP_ERR_UNSUPPORTED,
+              "mgp_fused_loo: shape not supported by the column kernel (k=%d d=%d r=%d)", p->k,
+              p->d, p->r);
+  MGP_REQUIRE(p->query_x == p->train_x && p->query_idx != nullptr, MGP_ERR_BAD_ARG,
+              "mgp_fused_loo expects a training batch: query_x == train_x and batch indices in "
+              "query_idx");
+  MGP_REQUIRE(ws != nullptr && ws_bytes >= loo_ws_bytes(), MGP_ERR_WORKSPACE,
+              "workspace of %zu bytes required", loo_ws_bytes());
+  MGP_REQUIRE(boundary_scale > 0.0 || loss_id != MGP_LOSS_PSEUDO_HUBER, MGP_ERR_BAD_ARG,
+              "boundary_scale must be positive");
+  ColLoo loo;
+  loo.counter = (unsigned int*)ws;
+  loo.warp_rec = (double*)((char*)ws + 256);
+  loo.partials = partials;
+  loo.loss_id = loss_id;
+  loo.boundary_scale = boundary_scale > 0.0 ? boundary_scale : 1.0;
+  int grid = 0;  // the full persistent grid, whatever the batch size (fixed summation order)
+  return launch_col(p, model, loo, &grid, (cudaStream_t)stream);
+}

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
 
-  const double tab64 = c_exp_tab[lane];
+  const double tab64 = a.exp_tab[lane];
   unsigned* etab = (unsigned*)smem;
   double* wbase = smem + (ROWS + 1) * 16 + (size_t)warp * warp_doubles;
   double* tiles = wbase;              // NT*64 image + 2 scratch doubles

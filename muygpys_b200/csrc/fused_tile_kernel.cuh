@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, SMEM_L ? 1 : 3)
   const int k = a.k, kp = a.kp, d = a.d, r = a.r;
 
   // CTA-shared: exp table and the table of the flat element list
-  const double tab64 = c_exp_tab[lane];  // this lane's entry of the 2^(j/32) table
+  const double tab64 = a.exp_tab[lane];  // this lane's entry of the 2^(j/32) table
   unsigned* etab = (unsigned*)smem;       // n_elem entries + 1 dummy
   const int etab_doubles = (((a.n_elem + 2) / 2) + 1) & ~1;
   double* sscale = smem + etab_doubles;  // gram mode: per-feature multipliers (anisotropic)

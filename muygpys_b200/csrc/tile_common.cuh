@@ -10,7 +10,6 @@ constexpr int TILE_WARPS = 4;        // warps (neighbourhoods in flight) per CTA
 constexpr int TILE_MAX_D = 8;
 constexpr int EXP_TABLE = 32;  // 2^(j/32), one entry per lane, looked up with a shuffle
 
-__constant__ double c_exp_tab[EXP_TABLE];  // 2^(j/32), correctly rounded on the host
 
 __device__ __forceinline__ double shfl_d(double v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
@@ -25,6 +24,10 @@ __device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, doubl
 
 // same instruction, not volatile: the scheduler may move it across other instructions
 __device__ __forceinline__ void dmma_free(double& c0, double& c1, double a, double b) {
+#ifdef MGP_DBG_NODMMA
+  c0 += a;
+  return;
+#endif
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
@@ -103,6 +106,10 @@ struct TileArgs {
   int aniso;       // coord_scale differs per feature
   double post_scale;               // F2 metric with Matern: s = post_scale * u2
   int kernel_id;
+  // 2^(j/32), correctly rounded on the host.  Lives in the kernel parameter space (not in a
+  // __constant__ symbol): parameters reach whichever device the launch targets, a symbol
+  // uploaded once per process only reached the device that was current at the time.
+  double exp_tab[EXP_TABLE];
 };
 
 // covariance as a function of u2 = sum of squared prescaled coordinate differences
@@ -211,17 +218,9 @@ static inline int tiles_needed(int k, int r) {
   return (kp + 1 + r + 7) / 8;
 }
 
-// Host: pack an mgp_problem + Model into TileArgs (and upload the exp table of THIS
-// translation unit on first use).
+// Host: pack an mgp_problem + Model into TileArgs.
 static inline int fill_tile_args(const mgp_problem* p, const Model& model, TileArgs& a) {
-  static bool table_ready = false;
-  if (!table_ready) {
-    double host_tab[EXP_TABLE];
-    for (int j = 0; j < EXP_TABLE; ++j) host_tab[j] = (double)exp2l((long double)j / EXP_TABLE);
-    cudaError_t e = cudaMemcpyToSymbol(c_exp_tab, host_tab, sizeof(host_tab));
-    MGP_REQUIRE(e == cudaSuccess, MGP_ERR_CUDA, "exp table upload: %s", cudaGetErrorString(e));
-    table_ready = true;
-  }
+  for (int j = 0; j < EXP_TABLE; ++j) a.exp_tab[j] = (double)exp2l((long double)j / EXP_TABLE);
   a.train_x = p->train_x;
   a.query_x = p->query_x;
   a.query_idx = p->query_idx;

@@ -59,6 +59,34 @@ def allreduce_partials(record: torch.Tensor, group=None) -> torch.Tensor:
     return record
 
 
+class PartialsReducer:
+    """Cross-rank SUM of 8-double partials records, delivered to the host.
+
+    One objective evaluation ends in exactly one of these reductions (two for looph and for
+    the analytic-scale nugget quirk).  `slot()` hands out the device record a kernel should
+    write into; `sum_to_host(record)` returns the summed record as numpy on every rank.  The
+    reduction is a plain `all_reduce(SUM)` on the process group (NCCL over NVLink on the GPU
+    box, gloo in the CPU tests); the copy to the host goes through one page-locked buffer."""
+
+    def __init__(self, device, group=None):
+        self.device = torch.device(device)
+        self.group = group
+        self._pin = None
+        if self.device.type == "cuda":
+            self._pin = torch.empty((8,), dtype=torch.float64).pin_memory()
+
+    def slot(self) -> torch.Tensor:
+        return torch.zeros((8,), dtype=torch.float64, device=self.device)
+
+    def sum_to_host(self, record: torch.Tensor):
+        allreduce_partials(record, self.group)
+        if self._pin is None:
+            return record.detach().cpu().numpy().copy()
+        self._pin.copy_(record, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._pin.numpy().copy()
+
+
 def allgather_rows(local: torch.Tensor, count: int, group=None) -> torch.Tensor:
     """Concatenate per-rank row chunks (uneven sizes allowed) in rank order --
     the analogue of `_consistent_unchunk_tensor` (S/_src/mpi_utils.py:118-143)."""

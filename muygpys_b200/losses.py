@@ -55,3 +55,20 @@ cross_entropy_fn = LossFn("cross_entropy", L.LOSS_CROSS_ENTROPY, False, lambda p
 pseudo_huber_fn = LossFn("pseudo_huber", L.LOSS_PSEUDO_HUBER, False, lambda p: p[L.P_AUX])
 lool_fn = LossFn("lool", L.LOSS_LOOL, True, lambda p: p[L.P_AUX])
 looph_fn = LossFn("looph", L.LOSS_LOOPH, True, lambda p: p[L.P_AUX])
+
+
+_REFERENCE_LOSS_NAMES = {"_mse_fn": mse_fn, "_cross_entropy_fn": cross_entropy_fn,
+                         "_pseudo_huber_fn": pseudo_huber_fn, "_lool_fn": lool_fn,
+                         "_looph_fn": looph_fn}
+
+
+def as_loss(loss_fn) -> LossFn:
+    """Our LossFn for either family of loss objects: a `MuyGPyS.optimize.loss.LossFn` wraps the
+    numpy-backend function in `._fn` (S/optimize/loss.py:205-213), whose name picks ours."""
+    if isinstance(loss_fn, LossFn):
+        return loss_fn
+    inner = getattr(loss_fn, "_fn", loss_fn)
+    ours = _REFERENCE_LOSS_NAMES.get(getattr(inner, "__name__", ""))
+    if ours is None:
+        raise NotImplementedError(f"loss function {loss_fn!r} is not on the fused path")
+    return ours

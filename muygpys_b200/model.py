@@ -19,7 +19,7 @@ from typing import Callable, List, Optional, Tuple
 import numpy as np
 import torch
 
-from . import ops
+from . import fused, ops
 from ._arrays import fdev, idev, like_input
 from .covariance import KernelFn
 from .hyperparameter import AnalyticScale, FixedScale, ScaleFn
@@ -147,82 +147,22 @@ class MuyGPS:
         host = (batch_indices, batch_nn_indices, train_features, train_targets)
         return crosswise, pairwise, like_input(batch_targets, *host), nn_targets
 
-    # ---- fused API (indices in, posterior out; K1) --------------------------
+    # ---- fused API (indices in, posterior out; K1): see fused.py ----------------
     def _fused(self, indices, nn_indices, test_features, train_features, train_targets, *,
                theta: Optional[dict] = None, scale: Optional[float] = None, **want):
-        theta = theta or {}
-        deformation = self.kernel.deformation
-        ls = deformation.length_scales(**theta)
-        nn = idev(nn_indices)
-        noise = self.noise.value(theta.get("noise"))
-        if test_features is None:
-            test_features = train_features
-        return ops.fused_posterior(
-            fdev(train_features), fdev(test_features),
-            None if indices is None else idev(indices), nn,
-            None if train_targets is None else fdev(train_targets),
-            kernel_id=self.kernel.kernel_id, metric_id=deformation.metric.metric_id,
-            length_scale=ls if deformation.anisotropic else ls[0], noise=noise,
-            scale=self.scale() if scale is None else scale, **want)
-
-    def _fused_pipelined(self, indices, nn_indices, test_features, train_features,
-                         train_targets, want_mean, want_var):
-        """Host-resident index batches: `mgp_fused_posterior_host` uploads chunk i+1 on a side
-        stream while chunk i is in the fused kernel, so the end-to-end rate is
-        max(PCIe, compute).  The chunk loop is native (csrc/pipeline.cu); a Python loop spent
-        more host time per chunk than the small first chunks take on the device."""
-        x, y = fdev(train_features), fdev(train_targets)
-        q_src = test_features if test_features is not None else train_features
-        q_h = torch.as_tensor(q_src)
-        # the query points are small next to the indices: one upload, then gather by index
-        q_dev = q_h if q_h.is_cuda else q_h.to(x.device, non_blocking=True)
-        deformation = self.kernel.deformation
-        ls = deformation.length_scales()
-        out = ops.fused_posterior_host(
-            x, q_dev, indices, nn_indices, y, kernel_id=self.kernel.kernel_id,
-            metric_id=deformation.metric.metric_id,
-            length_scale=ls if deformation.anisotropic else ls[0],
-            noise=self.noise.value(None), scale=self.scale(), want_mean=want_mean,
-            want_var=want_var)
-        return {"mean": out.get("mean"), "var": out.get("var")}
+        return fused.fused_call(self, indices, nn_indices, test_features, train_features,
+                                train_targets, theta=theta, scale=scale, **want)
 
     def fused_regress(self, indices, nn_indices, test_features, train_features, train_targets,
                       want_mean=True, want_var=True):
-        """Posterior mean and scaled variance straight from indices (one launch, or a
-        copy/compute pipeline when the index batch still lives in host memory)."""
-        from ._arrays import is_host
-
-        if (is_host(nn_indices) and not is_host(train_features) and not is_host(train_targets)
-                and not self.noise.heteroscedastic and len(nn_indices) >= 16384
-                and (indices is None or (test_features is not None and is_host(indices)))):
-            out = self._fused_pipelined(indices, nn_indices, test_features, train_features,
-                                        train_targets, want_mean, want_var)
-        else:
-            out = self._fused(indices, nn_indices, test_features, train_features,
-                              train_targets, want_mean=want_mean, want_var=want_var)
-        host = (indices, nn_indices, test_features, train_features, train_targets)
-        res = []
-        if want_mean:
-            res.append(like_input(_squeeze_response(out["mean"], fdev(train_targets)), *host))
-        if want_var:
-            res.append(like_input(out["var"], *host))
-        return tuple(res) if len(res) > 1 else res[0]
+        return fused.fused_regress(self, indices, nn_indices, test_features, train_features,
+                                   train_targets, want_mean=want_mean, want_var=want_var)
 
     def fused_fast_coefficients(self, nn_indices_fast, train_features, train_targets):
-        """(K+eps)^-1 Y for every row of `nn_indices_fast` (K3), never building Kin."""
-        out = self._fused(None, nn_indices_fast, train_features, train_features, train_targets,
-                          want_mean=False, want_var=False, want_coeffs=True)["coeffs"]
-        y = fdev(train_targets)
-        out = out[:, :, 0] if y.dim() == 1 else out
-        return like_input(out, nn_indices_fast, train_features, train_targets)
+        return fused.fused_fast_coefficients(self, nn_indices_fast, train_features,
+                                             train_targets)
 
     def fused_optimize_scale(self, batch_indices, batch_nn_indices, train_features,
                              train_targets):
-        """`optimize_scale` without materialising the pairwise tensor."""
-        if self.scale.analytic:
-            out = self._fused(batch_indices, batch_nn_indices, train_features, train_features,
-                              train_targets, want_mean=False, want_var=False, want_yky=True)
-            b, k = idev(batch_nn_indices).shape
-            self.scale._set(self.scale.from_mean_quadratic_form(float(out["yky"].sum()) / (b * k)))
-        self._make()
-        return self
+        return fused.fused_optimize_scale(self, batch_indices, batch_nn_indices, train_features,
+                                          train_targets)

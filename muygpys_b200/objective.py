@@ -1,10 +1,12 @@
 """Leave-one-out objective functions (S/optimize/objective.py:20-118, loss.py:26-178).
 
 `make_loo_crossval_fn` keeps the reference's signature and works on materialised
-difference/distance tensors through the staged kernels.  `make_fused_loo_crossval_fn`
-is the fast path: it captures (features, indices, targets) instead and every
-`obj_fn(**theta)` call is one K1 launch + one loss reduction, ending in a single
-8-double all-reduce when several ranks share the batch.
+difference/distance tensors through the staged kernels.  `make_fused_loo_crossval_fn` is the
+fast path: it captures (features, indices, targets) instead and, for one response with the mse,
+lool or pseudo-Huber loss, every `obj_fn(**theta)` call is ONE kernel launch
+(`mgp_fused_loo`: K1 with the loss / scale partials folded into its epilogue) followed by a
+64-byte read -- with several ranks, the per-rank records are summed by one all-reduce
+(`distributed.PartialsReducer`).  Other shapes take K1 + the loss kernels.
 """
 
 from __future__ import annotations
@@ -17,8 +19,10 @@ import torch
 from . import _lib as L
 from . import ops
 from ._arrays import fdev, idev
-from .distributed import allreduce_partials
-from .losses import LossFn
+from .adapt import ModelSpec
+from .distributed import PartialsReducer
+from .fused import fused_call
+from .losses import LossFn, as_loss
 
 
 def _finish_loss(loss_fn: LossFn, rec) -> float:
@@ -54,50 +58,104 @@ def make_loo_crossval_fn(loss_fn: LossFn, kernel_fn: Callable, mean_fn: Callable
     return obj_fn
 
 
-def make_fused_loo_crossval_fn(muygps, loss_fn: LossFn, batch_indices, batch_nn_indices,
+def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                                train_features, train_targets, target_mask=None,
                                loss_kwargs: Optional[Dict] = None, group=None,
                                distributed: bool = False) -> Callable:
     """Fused objective: nothing of size (b,k,k) is ever materialised.
 
-    With `distributed=True` the given batch rows are this rank's shard; partial
-    sums are combined across `group` so every rank returns the global objective.
+    `muygps` is a `MuyGPyS.gp.MuyGPS` or this package's mirror object, `loss_fn` a loss object
+    of either family.  With `distributed=True` the given batch rows are this rank's shard;
+    partial sums are combined across `group` so every rank returns the global objective.
     Accepts the keyword names the reference's optimiser uses: `length_scale` or
     `length_scale0..`, `noise`; anything else (e.g. `smoothness`) is ignored.
     """
+    spec = ModelSpec.of(muygps)
+    loss_fn = as_loss(loss_fn)
     loss_kwargs = dict(loss_kwargs or {})
     x = fdev(train_features)
     y = fdev(train_targets)
     bi, bnn = idev(batch_indices), idev(batch_nn_indices)
+    k = bnn.shape[1]
+    needs_var = loss_fn.needs_variance
+    analytic = needs_var and spec.analytic
+    delta = float(loss_kwargs.get("boundary_scale", loss_fn.default_boundary()))
+    model_noise = spec.noise(None)
+    d = 1 if x.dim() == 1 else x.shape[1]
+    r = 1 if y.dim() == 1 else y.shape[1]
+    reducer = PartialsReducer(x.device, group) if distributed else None
+
+    def same_noise(theta) -> bool:
+        noise_kw = theta.get("noise")
+        return noise_kw is None or spec.heteroscedastic or float(noise_kw) == float(model_noise)
+
+    def finish(rec, rec_scale=None) -> float:
+        """Loss value from the (summed) host record(s)."""
+        if not needs_var:
+            return float(_finish_loss(loss_fn, rec))
+        rows = rec[L.P_ROWS]
+        if analytic:
+            src = rec if rec_scale is None else rec_scale
+            sigma2 = spec.sigma_from_mean_quadratic_form(src[L.P_YKY] / (src[L.P_ROWS] * k))
+        else:
+            sigma2 = spec.scale()
+        # lool is affine in 1/sigma^2 and log sigma^2, so the sums of e^2/v, log v and
+        # y^T K^-1 y finish it after ONE reduction
+        return float(rec[L.P_SQERR_V] / sigma2 + rec[L.P_LOGV] + rows * math.log(sigma2))
+
+    one_launch = (target_mask is None
+                  and loss_fn.loss_id in (L.LOSS_MSE, L.LOSS_LOOL, L.LOSS_PSEUDO_HUBER)
+                  and ops.fused_loo_supported(d, k, r, spec.kernel_id, spec.metric_id,
+                                              spec.heteroscedastic)
+                  and x.data_ptr() % 16 == 0)
+    if one_launch:
+        loo = ops.FusedLoo(x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
+                           loss_id=loss_fn.loss_id, boundary_scale=delta,
+                           partials=None if reducer is None else reducer.slot())
+        loo_scale = []  # lazily: a second evaluator for the noise quirk below
+
+        def read(dev_rec):
+            return loo.record(dev_rec) if reducer is None else reducer.sum_to_host(dev_rec)
+
+        def obj_fn(*args, **theta):
+            ls = spec.length_scale_arg(**theta)
+            rec_scale = None
+            if analytic and not same_noise(theta):
+                # reference quirk: the analytic scale perturbs with the MODEL's nugget, ignoring
+                # the optimiser's `noise=` (S/gp/hyperparameter/scale.py:206-208)
+                if not loo_scale:
+                    loo_scale.append(ops.FusedLoo(
+                        x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
+                        loss_id=L.LOSS_NONE,
+                        partials=None if reducer is None else reducer.slot()))
+                rec_scale = read(loo_scale[0].launch(ls, model_noise))
+            rec = read(loo.launch(ls, spec.noise(theta.get("noise"))))
+            return -finish(rec, rec_scale)
+
+        return obj_fn
+
+    # ---- general shapes: K1, then the loss kernels ------------------------------------------
     y_b = y[bi].contiguous()
     if target_mask is not None:
         y_b = y_b[:, target_mask].contiguous()
-    k = bnn.shape[1]
-    needs_var = loss_fn.needs_variance
-    analytic = needs_var and muygps.scale.analytic
-    delta = float(loss_kwargs.get("boundary_scale", loss_fn.default_boundary()))
-    model_noise = muygps.noise.value(None)
-    reduce = (lambda rec: allreduce_partials(rec, group)) if distributed else (lambda rec: rec)
     rec_pin = torch.empty((L.MGP_PARTIALS,), dtype=torch.float64).pin_memory()
 
     def to_host(rec):
-        """The 8-double record through a page-locked buffer (cheaper than Tensor.cpu())."""
+        if reducer is not None:
+            return reducer.sum_to_host(rec)
         rec_pin.copy_(rec, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return rec_pin.numpy().copy()
 
     def obj_fn(*args, **theta):
-        noise_kw = theta.get("noise")
-        same_noise = noise_kw is None or muygps.noise.heteroscedastic or \
-            float(noise_kw) == float(model_noise)
-        out = muygps._fused(bi, bnn, x, x, y, theta=theta, scale=1.0, want_mean=True,
-                            want_var=needs_var, want_yky=analytic and same_noise)
+        same = same_noise(theta)
+        out = fused_call(spec, bi, bnn, x, x, y, theta=theta, scale=1.0, want_mean=True,
+                         want_var=needs_var, want_yky=analytic and same)
         yky = out.get("yky")
-        if analytic and not same_noise:
-            # reference quirk: the scale ignores the optimiser's nugget (scale.py:206-208)
+        if analytic and not same:
             th2 = {kk: v for kk, v in theta.items() if kk != "noise"}
-            yky = muygps._fused(bi, bnn, x, x, y, theta=th2, scale=1.0, want_mean=False,
-                                want_var=False, want_yky=True)["yky"]
+            yky = fused_call(spec, bi, bnn, x, x, y, theta=th2, scale=1.0, want_mean=False,
+                             want_var=False, want_yky=True)["yky"]
         mean = out["mean"]
         if y.dim() == 1:
             mean = mean[:, 0]
@@ -105,37 +163,20 @@ def make_fused_loo_crossval_fn(muygps, loss_fn: LossFn, batch_indices, batch_nn_
             mean = mean[:, target_mask].contiguous()
         if not needs_var:
             rec = ops.loss_partials(loss_fn.loss_id, mean, y_b, boundary_scale=delta)
-            rec = to_host(reduce(rec))
-            return -float(_finish_loss(loss_fn, rec))
+            return -finish(to_host(rec))
         var = out["var"]
+        if loss_fn.loss_id == L.LOSS_LOOL:
+            rec = ops.loss_partials(L.LOSS_LOOL, mean, y_b, var=var, yky=yky)
+            return -finish(to_host(rec))
+        # looph is nonlinear in sigma^2: reduce the scale first, then the loss
         if analytic:
-            if loss_fn.loss_id == L.LOSS_LOOL:
-                # lool is affine in 1/sigma^2 and log sigma^2, so the per-rank sums of
-                # e^2/v, log v and y^T K^-1 y finish it after ONE all-reduce
-                rec = ops.loss_partials(L.LOSS_LOOL, mean, y_b, var=var, yky=yky)
-                rec = to_host(reduce(rec))
-                rows = rec[L.P_ROWS]
-                sigma2 = muygps.scale.from_mean_quadratic_form(rec[L.P_YKY] / (rows * k))
-                loss = rec[L.P_SQERR_V] / sigma2 + rec[L.P_LOGV] + rows * math.log(sigma2)
-                return -float(loss)
-            # looph is nonlinear in sigma^2: reduce the scale first, then the loss
-            rec = reduce(ops.loss_partials(L.LOSS_NONE, mean, y_b, var=var, yky=yky))
-            sigma0 = rec[L.P_YKY] / (rec[L.P_ROWS] * k)
-            sigma2_dev = _iterate_scale(sigma0, muygps.scale.iteration_count).reshape(1)
+            rec = to_host(ops.loss_partials(L.LOSS_NONE, mean, y_b, var=var, yky=yky))
+            sigma2 = spec.sigma_from_mean_quadratic_form(rec[L.P_YKY] / (rec[L.P_ROWS] * k))
         else:
-            sigma2_dev = torch.full((1,), float(muygps.scale()), dtype=torch.float64,
-                                    device=mean.device)
+            sigma2 = spec.scale()
+        sigma2_dev = torch.full((1,), float(sigma2), dtype=torch.float64, device=mean.device)
         rec2 = ops.loss_partials(loss_fn.loss_id, mean, y_b, var=var, scale_dev=sigma2_dev,
                                  boundary_scale=delta)
-        rec2 = to_host(reduce(rec2))
-        return -float(rec2[L.P_AUX])
+        return -float(to_host(rec2)[L.P_AUX])
 
     return obj_fn
-
-
-def _iterate_scale(sigma0: torch.Tensor, iteration_count: int) -> torch.Tensor:
-    """Device-side twin of AnalyticScale.from_mean_quadratic_form (no host sync)."""
-    s = sigma0
-    for _ in range(1, iteration_count):
-        s = 0.5 * (s + sigma0 / s)
-    return s

@@ -29,6 +29,25 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its first CUDA tensor argument current, so that the
+    launch, the stream handle and every allocation target the tensors' device even when the
+    caller's current device is another GPU (one process may drive several)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+
+    return wrapped
+
+
 def _need_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise L.MgpError(
@@ -80,10 +99,12 @@ def as_2d(x: torch.Tensor) -> torch.Tensor:
 # fused path
 # --------------------------------------------------------------------------
 def set_fused_variant(variant: int) -> None:
-    """0 = auto, 1 = generic shared-memory kernel, 2 = register-tile DMMA kernel."""
+    """0 = auto, 1 = generic shared-memory kernel, 2 = register-tile DMMA kernel, 3 = pipelined
+    tile kernel, 4 = column-direct kernel."""
     L.check(L.lib().mgp_set_fused_variant(int(variant)))
 
 
+@_on_tensor_device
 def fused_posterior(
     train_x: torch.Tensor,
     query_x: torch.Tensor,
@@ -186,6 +207,7 @@ def fused_posterior(
     return out
 
 
+@_on_tensor_device
 def fused_posterior_host(train_x, query_x, query_idx_host, nn_idx_host, train_y, *,
                          mean_host: Optional[torch.Tensor] = None,
                          var_host: Optional[torch.Tensor] = None, **kw):
@@ -216,6 +238,78 @@ def fused_posterior_host(train_x, query_x, query_idx_host, nn_idx_host, train_y,
                            _host=(nn_h, idx_h, mean_host, var_host), **kw)
 
 
+class FusedLoo:
+    """One-launch leave-one-out objective evaluations over a fixed training batch.
+
+    Wraps `mgp_fused_loo`: everything that does not change between evaluations (device tensors,
+    the problem record, the zeroed workspace, the partials record and a page-locked copy of it)
+    is set up once; `launch(length_scale, noise)` then costs one kernel launch, and `record()`
+    one 64-byte device-to-host copy plus a stream synchronisation."""
+
+    @_on_tensor_device
+    def __init__(self, train_x, train_y, batch_idx, nn_idx, *, kernel_id, metric_id, loss_id,
+                 boundary_scale=1.0, partials: Optional[torch.Tensor] = None):
+        lib = L.lib()
+        self.x = as_2d(fdev(train_x, "train_features"))
+        y = fdev(train_y, "train_targets")
+        self.y = (y[:, None] if y.dim() == 1 else y).contiguous()
+        self.bi = idev(batch_idx, "batch_indices")
+        self.nn = idev(nn_idx, "batch_nn_indices")
+        n, d = self.x.shape
+        b, k = self.nn.shape
+        if self.y.shape[1] != 1:
+            raise NotImplementedError("mgp_fused_loo handles one response (r == 1)")
+        dev = self.x.device
+        self.ls_host = (C.c_double * max(d, 1))()
+        self.partials = partials if partials is not None else torch.zeros(
+            (L.MGP_PARTIALS,), dtype=f64, device=dev)
+        self.p = L.MgpProblem(
+            train_x=_p(self.x), query_x=_p(self.x), query_idx=_p(self.bi), nn_idx=_p(self.nn),
+            train_y=_p(self.y), n=n, t=n, b=b, k=k, d=d, r=1, kernel_id=int(kernel_id),
+            metric_id=int(metric_id), length_scale_count=1,
+            length_scale=C.cast(self.ls_host, C.POINTER(C.c_double)), noise=0.0, noise_bk=None,
+            scale=1.0, mean=None, var=None, yky=None, coeffs=None, status=None)
+        self.ws_bytes = lib.mgp_fused_loo_workspace_bytes(C.byref(self.p))
+        self.ws = torch.zeros((self.ws_bytes,), dtype=torch.uint8, device=dev)  # counter = 0
+        self.loss_id = int(loss_id)
+        self.boundary_scale = float(boundary_scale)
+        self.pinned = torch.empty((L.MGP_PARTIALS,), dtype=f64).pin_memory()
+        self._lib = lib
+
+    def launch(self, length_scale, noise: float) -> torch.Tensor:
+        """Enqueue one evaluation on the current stream; returns the device partials record."""
+        if self.x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(self.x.device):
+                return self.launch(length_scale, noise)
+        ls = _ls_list(length_scale)
+        for i, v in enumerate(ls):
+            self.ls_host[i] = v
+        self.p.length_scale_count = len(ls)
+        self.p.noise = float(noise)
+        L.check(self._lib.mgp_fused_loo(C.byref(self.p), self.loss_id, self.boundary_scale,
+                                        _p(self.partials), _p(self.ws), self.ws_bytes, _stream()))
+        return self.partials
+
+    def record(self, device_record: Optional[torch.Tensor] = None):
+        """Host copy (numpy, 8 doubles) of the partials record after a stream synchronise."""
+        self.pinned.copy_(self.partials if device_record is None else device_record,
+                          non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.pinned.numpy().copy()
+
+
+def fused_loo_supported(d: int, k: int, r: int, kernel_id: int, metric_id: int,
+                        heteroscedastic: bool) -> bool:
+    """Shapes `mgp_fused_loo` takes (mirrors fused_col_supported in csrc/fused_col.cu)."""
+    if r != 1 or d > 3 or heteroscedastic or not 6 <= k <= 62:
+        return False
+    if metric_id == L.METRIC_L2:
+        return kernel_id in (L.KERNEL_MATERN_05, L.KERNEL_MATERN_15, L.KERNEL_MATERN_25,
+                             L.KERNEL_MATERN_INF)
+    return kernel_id == L.KERNEL_RBF
+
+
+@_on_tensor_device
 def fast_mean(train_x, query_x, query_idx, nn_idx, coeff_row, coeffs, *, kernel_id, metric_id,
               length_scale) -> torch.Tensor:
     """K4: mean (b,r) = sum_j kernel(|q - x_nn_j|) * coeffs[coeff_row, j, :]."""
@@ -250,6 +344,7 @@ def fast_mean(train_x, query_x, query_idx, nn_idx, coeff_row, coeffs, *, kernel_
 # --------------------------------------------------------------------------
 # losses
 # --------------------------------------------------------------------------
+@_on_tensor_device
 def loss_partials(loss_id, pred, targets, var=None, yky=None, scale_dev=None,
                   boundary_scale=1.0, partials=None) -> torch.Tensor:
     """Accumulate an MGP_PARTIALS record (device tensor of 8 doubles)."""
@@ -278,6 +373,7 @@ def loss_partials(loss_id, pred, targets, var=None, yky=None, scale_dev=None,
 # --------------------------------------------------------------------------
 # KNN
 # --------------------------------------------------------------------------
+@_on_tensor_device
 def knn(train, queries, k, self_idx=None):
     lib = L.lib()
     train = as_2d(fdev(train, "train"))
@@ -305,6 +401,7 @@ class KnnGrid:
     POINTS_PER_CELL = 6.0  # measured: 4-8 is best for k = 10..100 (tools/sweep_grid_density.py)
     MAX_CELLS = 1 << 27
 
+    @_on_tensor_device
     def __init__(self, train: torch.Tensor):
         lib = L.lib()
         train = as_2d(fdev(train, "train"))
@@ -341,6 +438,7 @@ class KnnGrid:
         edges = torch.arange(ncells + 1, dtype=torch.int32, device=train.device)
         self.cell_start = torch.searchsorted(sorted_cell, edges).to(torch.int32).contiguous()
 
+    @_on_tensor_device
     def query(self, queries: torch.Tensor, k: int, self_idx=None):
         lib = L.lib()
         queries = as_2d(fdev(queries, "queries"))
@@ -367,6 +465,7 @@ class KnnGrid:
 # --------------------------------------------------------------------------
 # staged ops
 # --------------------------------------------------------------------------
+@_on_tensor_device
 def crosswise_diffs(data, nn_data, data_idx, nn_idx) -> torch.Tensor:
     lib = L.lib()
     data, nn_data = as_2d(fdev(data)), as_2d(fdev(nn_data))
@@ -380,6 +479,7 @@ def crosswise_diffs(data, nn_data, data_idx, nn_idx) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def pairwise_diffs(data, nn_idx) -> torch.Tensor:
     lib = L.lib()
     data = as_2d(fdev(data))
@@ -391,6 +491,7 @@ def pairwise_diffs(data, nn_idx) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def metric_reduce(metric_id, diffs, length_scale=None) -> torch.Tensor:
     lib = L.lib()
     diffs = fdev(diffs, "diffs")
@@ -411,6 +512,7 @@ def metric_reduce(metric_id, diffs, length_scale=None) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def crosswise_dists(metric_id, data, nn_data, data_idx, nn_idx) -> torch.Tensor:
     lib = L.lib()
     data, nn_data = as_2d(fdev(data)), as_2d(fdev(nn_data))
@@ -423,6 +525,7 @@ def crosswise_dists(metric_id, data, nn_data, data_idx, nn_idx) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def pairwise_dists(metric_id, data, nn_idx) -> torch.Tensor:
     lib = L.lib()
     data = as_2d(fdev(data))
@@ -434,6 +537,7 @@ def pairwise_dists(metric_id, data, nn_idx) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def kernel_apply(kernel_id, x, pre_scale=1.0) -> torch.Tensor:
     lib = L.lib()
     x = fdev(x, "dists")
@@ -443,6 +547,7 @@ def kernel_apply(kernel_id, x, pre_scale=1.0) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def perturb(Kin, noise) -> torch.Tensor:
     lib = L.lib()
     Kin = fdev(Kin, "Kin")
@@ -463,6 +568,7 @@ def perturb(Kin, noise) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def solve(Kin, Kcross=None, Y=None, kout=1.0, *, want_mean=False, want_var=False,
           want_yky=False, want_coeffs=False):
     """Batched SPD solve on materialised tensors (K5).  Y is (b,k) or (b,k,r)."""
@@ -496,6 +602,7 @@ def solve(Kin, Kcross=None, Y=None, kout=1.0, *, want_mean=False, want_var=False
     return out
 
 
+@_on_tensor_device
 def rowdot(Kcross, coeffs) -> torch.Tensor:
     lib = L.lib()
     Kcross = fdev(Kcross, "Kcross")

@@ -148,9 +148,8 @@ def test_staged_and_fused_regression(case):
 
 @pytest.mark.parametrize("case", [c for c in CASES if c.batch], ids=lambda c: c.name)
 def test_loo_objectives_staged_and_fused(case):
-    from muygpys_b200.optimize import L_BFGS_B_optimize
     from muygpys_b200.optimize import loss as losses
-    from muygpys_b200.optimize.objective import make_fused_loo_crossval_fn
+    from muygpys_b200.optimize.objective import make_fused_loo_crossval_fn, make_loo_crossval_fn
 
     m = _mods()
     g = load_golden(case.name)
@@ -163,8 +162,10 @@ def test_loo_objectives_staged_and_fused(case):
     for lname in case.losses:
         loss_fn = getattr(losses, f"{lname}_fn")
         want = g[f"obj_{lname}"]
-        staged = L_BFGS_B_optimize.make_obj_fn(muygps, b_t, b_nn_t, cwd, pwd, loss_fn=loss_fn,
-                                               loss_kwargs=case.loss_kwargs)
+        staged = make_loo_crossval_fn(loss_fn, muygps.kernel.get_opt_fn(),
+                                      muygps.get_opt_mean_fn(), muygps.get_opt_var_fn(),
+                                      muygps.get_opt_scale_fn(), pwd, cwd, b_nn_t, b_t,
+                                      loss_kwargs=case.loss_kwargs)
         fused = make_fused_loo_crossval_fn(muygps, loss_fn, bi, bnn, data["train_x"], targets,
                                            loss_kwargs=case.loss_kwargs)
         for fn, tag in ((staged, "staged"), (fused, "fused")):
@@ -186,7 +187,6 @@ def test_loo_objectives_staged_and_fused(case):
 @pytest.mark.parametrize("name", ["c1_rbf_1d", "c2_m15_2d", "c4_m25_aniso"])
 def test_lbfgsb_optimisation_recovers_reference_optimum(name):
     from muygpys_b200.examples.from_indices import optimize_from_indices
-    from muygpys_b200.optimize import L_BFGS_B_optimize
     from muygpys_b200.optimize.loss import mse_fn
 
     m = _mods()
@@ -196,8 +196,9 @@ def test_lbfgsb_optimisation_recovers_reference_optimum(name):
     targets = _targets(case, data)
     bi, bnn = data["batch_idx"], g["batch_nn_idx"]
     muygps = build_model(case, opt_bounds=True, scale=m["AnalyticScale"]())
-    opt = optimize_from_indices(muygps, bi, bnn, data["train_x"], targets, loss_fn=mse_fn,
-                                opt_fn=L_BFGS_B_optimize)
+    # the outer loop is the reference's own L_BFGS_B_optimize where MuyGPyS is importable (it is
+    # on the GPU box: baseline/_ref), scipy driven directly otherwise
+    opt = optimize_from_indices(muygps, bi, bnn, data["train_x"], targets, loss_fn=mse_fn)
     names, vals, _ = opt.get_opt_params()
     assert list(names) == [str(s) for s in g["opt_mse_names"]]
     # finite-difference L-BFGS-B: the path amplifies 1e-12 objective differences, the

@@ -91,3 +91,68 @@ def test_injected_reference_matches_plain_reference(name):
         row.append(model.scale.get_opt_fn(model)(model.kernel(pw), b_nn_t))
         vals.append(row)
     assert_close(np.array(vals[1]), np.array(vals[0]), 1e-10, "objectives and scale")
+
+
+@pytest.mark.parametrize("name", ["c2_m15_2d", "c4_m25_aniso", "c1_rbf_1d"])
+def test_fused_entry_points_take_genuine_reference_objects(name):
+    """A reference user changes ONE import (`MuyGPyS.examples.from_indices` ->
+    `muygpys_b200.examples.from_indices`) and keeps their own `MuyGPyS.gp.MuyGPS` object, loss
+    functor and optimiser: the fused one-launch path must give the plain reference's numbers."""
+    from MuyGPyS.examples import from_indices as ref_api
+    from MuyGPyS.gp import MuyGPS
+    from MuyGPyS.gp.deformation import F2, Anisotropy, Isotropy, l2
+    from MuyGPyS.gp.hyperparameter import AnalyticScale, Parameter, VectorParameter
+    from MuyGPyS.gp.kernels import RBF, Matern
+    from MuyGPyS.gp.noise import HomoscedasticNoise
+    from MuyGPyS.neighbors import NN_Wrapper
+    from MuyGPyS.optimize import L_BFGS_B_optimize
+    from MuyGPyS.optimize.loss import lool_fn, mse_fn
+
+    from muygpys_b200.examples import from_indices as our_api
+    from muygpys_b200.optimize.objective import make_fused_loo_crossval_fn
+
+    case = by_name(name)
+    data = make_data(case)
+    x, y, q = data["train_x"], data["train_y"][:, 0], data["test_x"]
+
+    def ls():
+        if case.anisotropic:
+            return VectorParameter(*[Parameter(v, (v * 0.1, v * 10)) for v in case.length_scale])
+        return Parameter(case.length_scale, (case.length_scale * 0.1, case.length_scale * 10))
+
+    if case.kernel_id == 0:
+        kernel = RBF(deformation=Isotropy(F2, ls()))
+    else:
+        nu = {1: 0.5, 2: 1.5, 3: 2.5}[case.kernel_id]
+        Def = Anisotropy if case.anisotropic else Isotropy
+        kernel = Matern(smoothness=Parameter(nu), deformation=Def(l2, ls()))
+    model = MuyGPS(kernel=kernel, noise=HomoscedasticNoise(case.noise), scale=AnalyticScale())
+    nbrs = NN_Wrapper(x, case.k, nn_method="exact", algorithm="ball_tree")
+    nn, _ = nbrs.get_nns(q)
+    t_idx = np.arange(case.t)
+    want_mean, want_var = ref_api.regress_from_indices(model, t_idx, nn, q, x, y)
+    got_mean, got_var = our_api.regress_from_indices(model, t_idx, nn, q, x, y)
+    assert isinstance(got_mean, np.ndarray)
+    assert_close(got_mean, want_mean, 1e-10, "fused mean from a reference object")
+    assert_close(got_var, want_var, 1e-10, "fused variance from a reference object")
+    assert_close(our_api.posterior_mean_from_indices(model, t_idx, nn, q, x, y), want_mean,
+                 1e-10, "posterior_mean_from_indices")
+    # objective: the reference's staged closure against the one-launch objective
+    bi = data["batch_idx"]
+    bnn, _ = nbrs.get_batch_nns(bi)
+    cw, pw, b_t, b_nn_t = model.make_train_tensors(bi, bnn, x, y)
+    kw = ({f"length_scale{i}": v * 1.3 for i, v in enumerate(case.length_scale)}
+          if case.anisotropic else {"length_scale": case.length_scale * 1.3})
+    for lf in (mse_fn, lool_fn):
+        want = L_BFGS_B_optimize.make_obj_fn(model, b_t, b_nn_t, cw, pw, loss_fn=lf)(**kw)
+        got = make_fused_loo_crossval_fn(model, lf, bi, bnn, x, y)(**kw)
+        assert_close(np.array([got]), np.array([want]), 1e-10, "fused objective")
+    # optimiser: the reference's L_BFGS_B_optimize loop around the fused objective returns a
+    # genuine MuyGPS with (nearly) the hyperparameters of the all-reference run
+    want_opt = ref_api.optimize_from_indices(model, bi, bnn, x, y, loss_fn=mse_fn,
+                                             opt_fn=L_BFGS_B_optimize)
+    got_opt = our_api.optimize_from_indices(model, bi, bnn, x, y, loss_fn=mse_fn,
+                                            opt_fn=L_BFGS_B_optimize)
+    assert type(got_opt) is MuyGPS
+    np.testing.assert_allclose(got_opt.get_opt_params()[1], want_opt.get_opt_params()[1],
+                               rtol=5e-3)
