@@ -137,11 +137,10 @@ int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_idx_host,
                              const int64_t* query_idx_host, double* mean_host,
                              double* var_host, void* ws, size_t ws_bytes, void* stream);
 
-/* Test/bench hook: 0 = choose automatically (column-direct > pipelined tile > tile > generic),
- * 1 = always the generic shared-memory kernel, 2 = the register-tile DMMA kernel where
- * supported, 3 = the software-pipelined tile kernel, 4 = the column-direct kernel (3 and 4:
- * error if the shape is unsupported).  Lets the independently written variants be
- * cross-checked on identical inputs. */
+/* Test/bench hook: 0 = choose automatically (column-direct > tile > generic), 1 = always the
+ * generic shared-memory kernel, 2 = the register-tile DMMA kernel where supported, 3 = the
+ * column-direct kernel (error if the shape is unsupported).  Lets the independently written
+ * variants be cross-checked on identical inputs. */
 int mgp_set_fused_variant(int32_t variant);
 
 /* One leave-one-out objective evaluation in ONE launch (a14-a16): the fused kernel over a
@@ -155,7 +154,7 @@ int mgp_set_fused_variant(int32_t variant);
  * sequence (S/optimize/objective.py:20-105, S/_src/optimize/loss/numpy.py:22-61,
  * S/_src/optimize/scale/numpy.py:9-15) for mse, lool and pseudo-Huber (MGP_LOSS_NONE gives the
  * scale partials only); looph is nonlinear in the analytic scale and keeps the two-pass path
- * (mgp_fused_posterior + mgp_loss_partials).  r == 1, d <= 3, k <= 62, homoscedastic nugget
+ * (mgp_fused_posterior + mgp_loss_partials).  r == 1, d <= 3, 7 <= k <= 62, homoscedastic nugget
  * (MGP_ERR_UNSUPPORTED otherwise).  `ws` must be ZERO-FILLED before its first use and handed
  * back unchanged afterwards (it carries a self-resetting arrival counter). */
 size_t mgp_fused_loo_workspace_bytes(const mgp_problem* p);

@@ -189,8 +189,6 @@ static int launch_generic(const mgp_problem* p, const Model& model, cudaStream_t
 }
 
 int fused_variant();
-int fused_pipe_supported(const mgp_problem* p, const Model& model);
-int launch_fused_pipe(const mgp_problem* p, const Model& model, cudaStream_t stream);
 int fused_col_supported(const mgp_problem* p, const Model& model);
 int launch_fused_col(const mgp_problem* p, const Model& model, cudaStream_t stream);
 int fused_tile_supported(const mgp_problem* p, const Model& model);
@@ -228,16 +226,10 @@ extern "C" int mgp_fused_posterior(const mgp_problem* p, void* ws, size_t ws_byt
   if (rc != MGP_OK) return rc;
   if (p->b == 0) return MGP_OK;
   const int variant = mgp::fused_variant();
-  if ((variant == 0 || variant == 4) && mgp::fused_col_supported(p, model))
+  if ((variant == 0 || variant == 3) && mgp::fused_col_supported(p, model))
     return mgp::launch_fused_col(p, model, (cudaStream_t)stream);
-  if (variant == 4) {
-    mgp::set_error("the column-direct kernel does not support this shape");
-    return MGP_ERR_UNSUPPORTED;
-  }
-  if ((variant == 0 || variant == 3) && mgp::fused_pipe_supported(p, model))
-    return mgp::launch_fused_pipe(p, model, (cudaStream_t)stream);
   if (variant == 3) {
-    mgp::set_error("the pipelined tile kernel does not support this shape");
+    mgp::set_error("the column-direct kernel does not support this shape");
     return MGP_ERR_UNSUPPORTED;
   }
   if (mgp::fused_tile_supported(p, model))

@@ -1,4 +1,4 @@
-// Device helpers shared by the register-tile fused kernels (fused_tile.cu, fused_pipe.cu).
+// Device helpers shared by the register-tile fused kernels (fused_tile*.cu, fused_col*.cu).
 #pragma once
 
 #include "common.cuh"

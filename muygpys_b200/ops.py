@@ -99,8 +99,8 @@ def as_2d(x: torch.Tensor) -> torch.Tensor:
 # fused path
 # --------------------------------------------------------------------------
 def set_fused_variant(variant: int) -> None:
-    """0 = auto, 1 = generic shared-memory kernel, 2 = register-tile DMMA kernel, 3 = pipelined
-    tile kernel, 4 = column-direct kernel."""
+    """0 = auto, 1 = generic shared-memory kernel, 2 = register-tile DMMA kernel, 3 = the
+    column-direct kernel."""
     L.check(L.lib().mgp_set_fused_variant(int(variant)))
 
 
@@ -301,7 +301,7 @@ class FusedLoo:
 def fused_loo_supported(d: int, k: int, r: int, kernel_id: int, metric_id: int,
                         heteroscedastic: bool) -> bool:
     """Shapes `mgp_fused_loo` takes (mirrors fused_col_supported in csrc/fused_col.cu)."""
-    if r != 1 or d > 3 or heteroscedastic or not 6 <= k <= 62:
+    if r != 1 or d > 3 or heteroscedastic or not 7 <= k <= 62:
         return False
     if metric_id == L.METRIC_L2:
         return kernel_id in (L.KERNEL_MATERN_05, L.KERNEL_MATERN_15, L.KERNEL_MATERN_25,

@@ -146,6 +146,35 @@ def test_staged_and_fused_regression(case):
     np.testing.assert_array_equal(cmean, fmean)
 
 
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_regress_any_features_in_posterior_out(case):
+    """regress_any (S/examples/regress.py:602-668): KNN on the device feeding the fused kernel,
+    the neighbour indices never leave the GPU; equals the golden mean / variance produced by the
+    reference from ITS neighbours."""
+    from muygpys_b200.examples.regress import regress_any
+    from muygpys_b200.neighbors import NN_Wrapper
+
+    g = load_golden(case.name)
+    data = make_data(case)
+    targets = _targets(case, data)
+    if case.hetero:
+        pytest.skip("heteroscedastic noise is indexed by precomputed neighbours")
+    scale = _mods()["FixedScale"]()
+    scale._set(float(g["scale_val"]))
+    muygps = build_model(case, scale=scale)
+    nbrs = NN_Wrapper(data["train_x"], case.k)
+    mean, var, timing = regress_any(muygps, data["test_x"], data["train_x"], nbrs, targets)
+    assert isinstance(mean, np.ndarray) and set(timing) == {"nn", "agree", "pred"}
+    assert_close(mean, g["mean"], RTOL, "regress_any mean")
+    assert_close(var, g["var"], RTOL, "regress_any variance")
+    # device tensors in -> device tensors out, no host round trip
+    dmean, dvar, _ = regress_any(muygps, torch.as_tensor(data["test_x"]).cuda(),
+                                 torch.as_tensor(data["train_x"]).cuda(), nbrs,
+                                 torch.as_tensor(targets).cuda())
+    assert dmean.is_cuda and dvar.is_cuda
+    np.testing.assert_array_equal(dmean.cpu().numpy(), mean)
+
+
 @pytest.mark.parametrize("case", [c for c in CASES if c.batch], ids=lambda c: c.name)
 def test_loo_objectives_staged_and_fused(case):
     from muygpys_b200.optimize import loss as losses

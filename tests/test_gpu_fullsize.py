@@ -81,7 +81,7 @@ def test_c2_fused_kernels_agree_and_match_oracle(c2):
 
     kw = dict(kernel_id=O.KERNEL_MATERN_15, metric_id=O.METRIC_L2, length_scale=0.1, noise=1e-3,
               want_yky=True, want_status=True)
-    ops.set_fused_variant(3)  # software-pipelined tile kernel (the one bench.py times)
+    ops.set_fused_variant(3)  # column-direct kernel (the one bench.py times)
     tile = ops.fused_posterior(c2["xd"], c2["qd"], None, c2["nn"], c2["yd"], **kw)
     again = ops.fused_posterior(c2["xd"], c2["qd"], None, c2["nn"], c2["yd"], **kw)
     ops.set_fused_variant(2)  # plain tile kernel
@@ -92,8 +92,8 @@ def test_c2_fused_kernels_agree_and_match_oracle(c2):
     assert int(tile["status"].sum()) == 0 and int(gen["status"].sum()) == 0
     for key in ("mean", "var", "yky"):
         assert torch.equal(tile[key], again[key]), f"{key} not bitwise reproducible"
-        assert_close(tile[key].cpu().numpy(), gen[key].cpu().numpy(), RTOL, f"pipe vs generic {key}")
-        assert_close(tile[key].cpu().numpy(), plain[key].cpu().numpy(), RTOL, f"pipe vs tile {key}")
+        assert_close(tile[key].cpu().numpy(), gen[key].cpu().numpy(), RTOL, f"column vs generic {key}")
+        assert_close(tile[key].cpu().numpy(), plain[key].cpu().numpy(), RTOL, f"column vs tile {key}")
     var = tile["var"].cpu().numpy()
     assert np.all(var > 0.0) and np.all(var <= 1.0 + 1e-12), "unscaled variance must lie in (0,1]"
     rows = np.random.default_rng(7).choice(100_000, 400, replace=False)

@@ -33,9 +33,9 @@ def _2d(x):
 @pytest.fixture(scope="module", params=["auto", "tile", "generic"])
 def ops(request):
     """Every test runs three times: through the automatically chosen fused kernel (the
-    software-pipelined tile kernel where the shape allows, else the tile kernel), with the
-    pipelined variant disabled, and through the generic shared-memory kernel -- independently
-    written implementations of the same contract."""
+    column-direct kernel where the shape allows, else the tile kernel), through the tile kernel
+    and through the generic shared-memory kernel -- independently written implementations of
+    the same contract."""
     from muygpys_b200 import ops as _ops
 
     _ops.set_fused_variant({"auto": 0, "tile": 2, "generic": 1}[request.param])
@@ -527,3 +527,123 @@ def test_high_dimensional_gram_training_batch_heteroscedastic(d):
         assert_close(out["mean"].cpu().numpy(), want_mean, RTOL, f"{name} mean d={d}")
         assert_close(out["var"].cpu().numpy(), want_var, RTOL, f"{name} var d={d}")
         assert_close(out["yky"].cpu().numpy(), want_yky, RTOL, f"{name} yky d={d}")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_kernels_follow_their_tensors_to_a_second_device():
+    """One process, two GPUs: launches, the exp table (kernel parameters) and the cached device
+    attributes must follow the tensors' device, not the current one (r1 advisor finding: a
+    per-process constant table left device 1 with zeros -> mean 0, var = scale, no error)."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(3)
+    n, b, k = 3000, 500, 50
+    xh, yh, qh = rng.uniform(size=(n, 2)), rng.normal(size=n), rng.uniform(size=(b, 2))
+    outs = []
+    for dev in (0, 1):
+        x, y, q = (torch.as_tensor(a).to(f"cuda:{dev}") for a in (xh, yh, qh))
+        torch.cuda.set_device(0)  # the CURRENT device stays 0 throughout
+        nn, _ = ops.knn(x, q, k)
+        assert nn.device.index == dev
+        for variant in (3, 2, 1):
+            ops.set_fused_variant(variant)
+            out = ops.fused_posterior(x, q, None, nn, y, kernel_id=2, metric_id=0,
+                                      length_scale=0.1, noise=1e-3)
+            assert out["mean"].device.index == dev
+            outs.append((dev, variant, out["mean"].cpu().numpy(), out["var"].cpu().numpy()))
+    ops.set_fused_variant(0)
+    for dev, variant, mean, var in outs[1:]:
+        np.testing.assert_allclose(mean, outs[0][2], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(var, outs[0][3], rtol=0, atol=1e-11)
+        assert np.abs(mean).max() > 1e-3
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_column_kernel_shape_sweep(d):
+    """The column-direct kernel (variant 3, forced: an unsupported shape would raise) against
+    the numpy oracle for every neighbour count around its tile boundaries -- the augmented rows
+    (cross-covariance, targets) move through the last two tile rows as k changes -- and every
+    covariance function it builds, prediction and training-batch (query_idx) forms."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(40 + d)
+    n, b = 1500, 64
+    x = rng.uniform(size=(n, d))
+    y = rng.normal(size=(n, 1))
+    q = rng.uniform(size=(b, d))
+    x[7] = x[3]  # an exact duplicate: zero distance inside neighbourhoods
+    ks = [7, 8, 9, 14, 15, 16, 22, 23, 30, 31, 38, 39, 46, 47, 50, 54, 55, 62]
+    try:
+        for k in ks:
+            nn, _ = O.knn_exact(x, q, k)
+            kid = int(rng.integers(0, 5))
+            metric = O.METRIC_F2 if kid == O.KERNEL_RBF else O.METRIC_L2
+            ls = rng.uniform(0.2, 0.5, size=d) if (d > 1 and k % 2) else 0.3
+            kw = dict(kernel_id=kid, metric_id=metric, length_scale=ls, noise=1e-3, scale=1.3,
+                      want_yky=True, want_status=True)
+            ops.set_fused_variant(3)
+            got = ops.fused_posterior(dev(x), dev(q), None, dev(nn), dev(y), **kw)
+            ops.set_fused_variant(1)
+            ref = ops.fused_posterior(dev(x), dev(q), None, dev(nn), dev(y), **kw)
+            assert int(got["status"].sum()) == 0
+            want_mean, want_var = O.predict(kid, metric, ls, 1e-3, 1.3, x, y[:, 0], q,
+                                            np.arange(b), nn)
+            assert_close(got["mean"].cpu().numpy()[:, 0], want_mean, RTOL, f"mean k={k} d={d}")
+            assert_close(got["var"].cpu().numpy(), want_var, RTOL, f"var k={k} d={d}")
+            assert_close(got["yky"].cpu().numpy(), ref["yky"].cpu().numpy(), RTOL, f"yky k={k}")
+        # training-batch form: queries are rows of the training set
+        k = 50
+        bi = np.sort(rng.choice(n, b, replace=False))
+        bnn, _ = O.knn_exact(x, x[bi], k + 1)
+        bnn = np.ascontiguousarray(bnn[:, 1:])
+        ops.set_fused_variant(3)
+        got = ops.fused_posterior(dev(x), dev(x), dev(bi), dev(bnn), dev(y), kernel_id=2,
+                                  metric_id=0, length_scale=0.3, noise=1e-3)
+        want_mean, want_var = O.predict(2, 0, 0.3, 1e-3, 1.0, x, y[:, 0], x, bi, bnn)
+        assert_close(got["mean"].cpu().numpy()[:, 0], want_mean, RTOL, "batch mean")
+        assert_close(got["var"].cpu().numpy(), want_var, RTOL, "batch var")
+        # a non-positive pivot is reported, not hidden: negative nugget on duplicated points
+        nn, _ = O.knn_exact(x, x[[3]], 10)
+        bad = ops.fused_posterior(dev(x), dev(x[[3]]), None, dev(nn), dev(y), kernel_id=2,
+                                  metric_id=0, length_scale=0.3, noise=-1e-3, want_status=True)
+        assert int(bad["status"][0]) == 1 and bool(torch.isnan(bad["mean"]).all())
+    finally:
+        ops.set_fused_variant(0)
+
+
+@pytest.mark.parametrize("loss_id,k,d", [(1, 50, 2), (2, 50, 2), (4, 30, 1), (2, 23, 3), (0, 62, 2)])
+def test_fused_loo_record_matches_two_pass_path(loss_id, k, d):
+    """mgp_fused_loo (K1 with the loss / scale partials in its epilogue, one launch) against
+    K1 + mgp_loss_partials on the same batch, slot by slot; repeated launches reuse the
+    self-resetting workspace and are bit-reproducible."""
+    from muygpys_b200 import _lib as L
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(loss_id * 100 + k)
+    n, b = 5000, 1237
+    x = dev(rng.uniform(size=(n, d)))
+    y = dev(np.sin(3 * rng.uniform(size=n)) + 0.1 * rng.normal(size=n))
+    bi = dev(np.sort(rng.choice(n, b, replace=False)))
+    nn, _ = ops.knn(x, x[bi], k + 1)
+    nn = nn[:, 1:].contiguous()
+    kid, ls, noise = (2, 0.2, 1e-3) if d > 1 else (0, 0.05, 1e-3)
+    mid = 1 if kid == 0 else 0
+    loo = ops.FusedLoo(x, y, bi, nn, kernel_id=kid, metric_id=mid, loss_id=loss_id,
+                       boundary_scale=1.5)
+    rec = loo.record(loo.launch(ls, noise))
+    out = ops.fused_posterior(x, x, bi, nn, y, kernel_id=kid, metric_id=mid, length_scale=ls,
+                              noise=noise, want_yky=True)
+    two_pass = ops.loss_partials(loss_id, out["mean"][:, 0].contiguous(), y[bi].contiguous(),
+                                 var=out["var"], yky=out["yky"], boundary_scale=1.5)
+    want = two_pass.cpu().numpy()
+    assert rec[L.P_ROWS] == b and rec[L.P_COUNT] == b and rec[L.P_BAD] == 0
+    slots = [L.P_SQERR, L.P_YKY]
+    slots += [L.P_SQERR_V, L.P_LOGV] if loss_id == 2 else []
+    slots += [L.P_AUX] if loss_id == 4 else []
+    for s_ in slots:
+        assert abs(rec[s_] - want[s_]) <= 1e-11 * abs(want[s_]), (s_, rec[s_], want[s_])
+    for _ in range(3):  # same launch again: identical bits (fixed summation order)
+        again = loo.record(loo.launch(ls, noise))
+        np.testing.assert_array_equal(again, rec)
+    other = loo.record(loo.launch(ls * 1.5, noise * 2))
+    assert other[L.P_SQERR] != rec[L.P_SQERR]

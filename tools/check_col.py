@@ -23,7 +23,7 @@ for d in (2, 1, 3):
                       want_yky=True, want_status=True)
             ops.set_fused_variant(2)
             ref = ops.fused_posterior(x, q, None, nn, y, **kw)
-            ops.set_fused_variant(4)
+            ops.set_fused_variant(3)
             got = ops.fused_posterior(x, q, None, nn, y, **kw)
             for name in ("mean", "var", "yky"):
                 r_, g_ = ref[name].flatten(), got[name].flatten()
@@ -44,7 +44,7 @@ nn, _ = ops.knn(x, x[bi], k + 1)
 nn = nn[:, 1:].contiguous()
 kw = dict(kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3, want_yky=True)
 ops.set_fused_variant(2); ref = ops.fused_posterior(x, x, bi, nn, y, **kw)
-ops.set_fused_variant(4); got = ops.fused_posterior(x, x, bi, nn, y, **kw)
+ops.set_fused_variant(3); got = ops.fused_posterior(x, x, bi, nn, y, **kw)
 for name in ("mean", "var", "yky"):
     print("loo", name, float((ref[name] - got[name]).abs().max() / ref[name].abs().max()))
 
@@ -58,7 +58,7 @@ nn, _ = NN_Wrapper(x, k).get_nns(q)
 nn = torch.as_tensor(nn).cuda() if not torch.is_tensor(nn) else nn
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 res = {}
-for variant in (3, 2, 4):
+for variant in (2, 3):
     ops.set_fused_variant(variant)
     f = lambda: ops.fused_posterior(x, q, None, nn, y, kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3)
     for _ in range(3): f()
@@ -71,7 +71,7 @@ for variant in (3, 2, 4):
     res[f"v{variant}"] = {"ms": float(np.mean(ts)), "min_ms": min(ts), "Mnbhd_s": b / np.mean(ts) / 1e3}
 for kk in (30, 40, 46, 54, 62):
     nn2 = torch.randint(0, n, (b, kk), device="cuda")
-    for variant in (2, 4):
+    for variant in (2, 3):
         ops.set_fused_variant(variant)
         f = lambda: ops.fused_posterior(x, q, None, nn2, y, kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3)
         f(); torch.cuda.synchronize()
