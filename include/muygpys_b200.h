@@ -33,6 +33,7 @@ extern "C" {
 #define MGP_VERSION 100 /* 0.1.0 */
 #define MGP_MAX_ANISO_DIM 32 /* anisotropic length scales live in kernel params */
 #define MGP_PARTIALS 8       /* doubles in a loss/scale partials record */
+#define MGP_MAX_PEERS 8      /* GPUs of one NVLink domain that can share a partials record */
 
 typedef enum mgp_status {
   MGP_OK = 0,
@@ -160,6 +161,32 @@ int mgp_set_fused_variant(int32_t variant);
 size_t mgp_fused_loo_workspace_bytes(const mgp_problem* p);
 int mgp_fused_loo(const mgp_problem* p, int32_t loss_id, double boundary_scale,
                   double* partials, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- cross-GPU SUM of a partials record over NVLink peer memory --------------------------
+ * The replacement for the reference's allreduce sites on this path (S/_src/optimize/loss/mpi.py
+ * :21-104, S/_src/optimize/scale/mpi.py:19-37) when the ranks are GPUs of one NVLink /
+ * NVSwitch domain.  Every rank allocates a peer-mapped buffer of mgp_peer_buffer_bytes() bytes,
+ * ZERO-FILLED once (symmetric memory; the Python side uses
+ * torch.distributed._symmetric_memory), and fills `peer_buf[p]` with rank p's buffer as mapped
+ * into THIS process.  `epoch` must start at 1 and increase by one per call on every rank.
+ * The record is pushed into every peer's buffer with 8-byte P2P stores, a release flag
+ * follows, and each rank adds the records in rank order once all flags of this epoch have
+ * arrived: one block, no separate collective launch, bit-identical sums on every rank.  A peer
+ * that does not arrive within ~2 s poisons the result with NaN instead of hanging the GPU. */
+typedef struct mgp_peer_group {
+  int32_t rank, world;          /* world <= MGP_MAX_PEERS */
+  uint64_t epoch;
+  void* peer_buf[MGP_MAX_PEERS];
+} mgp_peer_group;
+size_t mgp_peer_buffer_bytes(void);
+/* partials (MGP_PARTIALS doubles, device): local record in, global sum out. */
+int mgp_peer_sum8(double* partials, const mgp_peer_group* g, void* stream);
+/* mgp_fused_loo with the cross-GPU sum fused into the epilogue of the SAME kernel: the last
+ * block to finish reduces the per-warp records and then runs the peer exchange; `partials`
+ * receives the sum over all ranks.  g == NULL or g->world == 1 behaves like mgp_fused_loo. */
+int mgp_fused_loo_peers(const mgp_problem* p, int32_t loss_id, double boundary_scale,
+                        double* partials, void* ws, size_t ws_bytes, const mgp_peer_group* g,
+                        void* stream);
 
 /* ---- losses and scale partials (a14/a15) -------------------------------
  * Accumulates (adds) a partials record over b rows into `partials`

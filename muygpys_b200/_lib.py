@@ -22,6 +22,7 @@ MGP_ERR_UNSUPPORTED = -2
 MGP_ERR_CUDA = -3
 MGP_ERR_WORKSPACE = -4
 MGP_PARTIALS = 8
+MGP_MAX_PEERS = 8
 MGP_MAX_ANISO_DIM = 32
 
 # enums (mgp_kernel_id, mgp_metric_id, mgp_loss_id, partial slots)
@@ -49,7 +50,15 @@ class MgpProblem(C.Structure):
     ]
 
 
+class MgpPeerGroup(C.Structure):
+    """Mirror of `struct mgp_peer_group`."""
+
+    _fields_ = [("rank", _i32), ("world", _i32), ("epoch", C.c_uint64),
+                ("peer_buf", C.c_void_p * 8)]
+
+
 _PP = C.POINTER(MgpProblem)
+_PG = C.POINTER(MgpPeerGroup)
 _HOSTD = C.POINTER(C.c_double)
 
 # name -> (restype, argtypes); must list every symbol the header declares
@@ -62,6 +71,9 @@ SIGNATURES = {
     "mgp_set_fused_variant": (C.c_int, [_i32]),
     "mgp_fused_loo_workspace_bytes": (_sz, [_PP]),
     "mgp_fused_loo": (C.c_int, [_PP, _i32, _f64, _dp, _dp, _sz, _dp]),
+    "mgp_peer_buffer_bytes": (_sz, []),
+    "mgp_peer_sum8": (C.c_int, [_dp, _PG, _dp]),
+    "mgp_fused_loo_peers": (C.c_int, [_PP, _i32, _f64, _dp, _dp, _sz, _PG, _dp]),
     "mgp_loss_workspace_bytes": (_sz, [_i64, _i32]),
     "mgp_loss_partials": (C.c_int, [_i32, _dp, _dp, _dp, _dp, _dp, _f64, _i64, _i32, _dp, _dp,
                                     _sz, _dp]),

@@ -67,8 +67,50 @@ extern "C" size_t mgp_fused_loo_workspace_bytes(const mgp_problem* p) {
   return mgp::loo_ws_bytes();
 }
 
+namespace mgp {
+
+static int check_peers(const mgp_peer_group* g) {
+  MGP_REQUIRE(g->world >= 1 && g->world <= MGP_MAX_PEERS && g->rank >= 0 && g->rank < g->world,
+              MGP_ERR_BAD_ARG, "peer group: rank %d of %d (at most %d peers)", g->rank, g->world,
+              MGP_MAX_PEERS);
+  MGP_REQUIRE(g->epoch >= 1, MGP_ERR_BAD_ARG, "peer group: epochs start at 1");
+  for (int p = 0; p < g->world; ++p)
+    MGP_REQUIRE(g->peer_buf[p] != nullptr, MGP_ERR_BAD_ARG, "peer group: buffer %d is NULL", p);
+  return MGP_OK;
+}
+
+__global__ void __launch_bounds__(64) peer_sum8_kernel(double* partials, const mgp_peer_group g) {
+  __shared__ double rec[MGP_PARTIALS];
+  if (threadIdx.x < MGP_PARTIALS) rec[threadIdx.x] = partials[threadIdx.x];
+  __syncthreads();
+  peer_sum8_block(g, rec, partials);
+}
+
+}  // namespace mgp
+
+extern "C" size_t mgp_peer_buffer_bytes(void) {
+  return mgp::PEER_DATA_DOUBLES * sizeof(double) +
+         2 * MGP_MAX_PEERS * sizeof(unsigned long long);
+}
+
+extern "C" int mgp_peer_sum8(double* partials, const mgp_peer_group* g, void* stream) {
+  using namespace mgp;
+  MGP_REQUIRE(partials && g, MGP_ERR_BAD_ARG, "partials and peer group are required");
+  const int rc = check_peers(g);
+  if (rc != MGP_OK) return rc;
+  if (g->world == 1) return MGP_OK;
+  peer_sum8_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(partials, *g);
+  return check_launch("peer_sum8_kernel");
+}
+
 extern "C" int mgp_fused_loo(const mgp_problem* p, int32_t loss_id, double boundary_scale,
                              double* partials, void* ws, size_t ws_bytes, void* stream) {
+  return mgp_fused_loo_peers(p, loss_id, boundary_scale, partials, ws, ws_bytes, nullptr, stream);
+}
+
+extern "C" int mgp_fused_loo_peers(const mgp_problem* p, int32_t loss_id, double boundary_scale,
+                                   double* partials, void* ws, size_t ws_bytes,
+                                   const mgp_peer_group* g, void* stream) {
   using namespace mgp;
   int rc = validate_problem(p);
   if (rc != MGP_OK) return rc;
@@ -92,7 +134,14 @@ extern "C" int mgp_fused_loo(const mgp_problem* p, int32_t loss_id, double bound
               "workspace of %zu bytes required", loo_ws_bytes());
   MGP_REQUIRE(boundary_scale > 0.0 || loss_id != MGP_LOSS_PSEUDO_HUBER, MGP_ERR_BAD_ARG,
               "boundary_scale must be positive");
-  ColLoo loo;
+  ColLoo loo = {};
+  if (g != nullptr && g->world > 1) {
+    rc = check_peers(g);
+    if (rc != MGP_OK) return rc;
+    loo.peers = *g;
+  } else {
+    loo.peers.world = 1;
+  }
   loo.counter = (unsigned int*)ws;
   loo.warp_rec = (double*)((char*)ws + 256);
   loo.partials = partials;

@@ -35,6 +35,7 @@
 
 #include <type_traits>
 
+#include "peer_sum.cuh"
 #include "tile_common.cuh"
 
 namespace mgp {
@@ -46,6 +47,7 @@ struct ColLoo {
   unsigned int* counter;   // arrival counter (self-resetting)
   int loss_id;
   double boundary_scale;
+  mgp_peer_group peers;    // world > 1: sum the record across GPUs in the same kernel
 };
 
 namespace {
@@ -566,13 +568,20 @@ __global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
         s += __ldcg(loo.warp_rec + (size_t)w * MGP_PARTIALS + slot);
       s_red[grp][slot] = s;
       __syncthreads();
+      __shared__ double s_tot[MGP_PARTIALS];
       if (threadIdx.x < MGP_PARTIALS) {
         double tot = 0.0;
 #pragma unroll
         for (int g = 0; g < 16; ++g) tot += s_red[g][threadIdx.x];
-        loo.partials[threadIdx.x] = tot;
+        s_tot[threadIdx.x] = tot;
+        if (loo.peers.world <= 1) loo.partials[threadIdx.x] = tot;
       }
       if (threadIdx.x == 0) *loo.counter = 0u;  // ready for the next launch
+      if (loo.peers.world > 1) {
+        // cross-GPU sum over NVLink peer memory, still inside this kernel
+        __syncthreads();
+        peer_sum8_block(loo.peers, s_tot, loo.partials);
+      }
     }
   }
 }

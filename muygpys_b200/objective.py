@@ -113,9 +113,14 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                            loss_id=loss_fn.loss_id, boundary_scale=delta,
                            partials=None if reducer is None else reducer.slot())
         loo_scale = []  # lazily: a second evaluator for the noise quirk below
+        # several GPUs: the kernel's own epilogue sums the records over NVLink peer memory
+        chan = None if reducer is None else reducer.channel()
+        chan_scale = None if reducer is None else reducer.channel()
 
-        def read(dev_rec):
-            return loo.record(dev_rec) if reducer is None else reducer.sum_to_host(dev_rec)
+        def read(dev_rec, fused_sum):
+            if reducer is None:
+                return loo.record(dev_rec)
+            return reducer.to_host(dev_rec) if fused_sum else reducer.sum_to_host(dev_rec)
 
         def obj_fn(*args, **theta):
             ls = spec.length_scale_arg(**theta)
@@ -128,8 +133,9 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                         x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
                         loss_id=L.LOSS_NONE,
                         partials=None if reducer is None else reducer.slot()))
-                rec_scale = read(loo_scale[0].launch(ls, model_noise))
-            rec = read(loo.launch(ls, spec.noise(theta.get("noise"))))
+                rec_scale = read(loo_scale[0].launch(ls, model_noise, chan_scale),
+                                 chan_scale is not None)
+            rec = read(loo.launch(ls, spec.noise(theta.get("noise")), chan), chan is not None)
             return -finish(rec, rec_scale)
 
         return obj_fn

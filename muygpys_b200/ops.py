@@ -276,18 +276,22 @@ class FusedLoo:
         self.pinned = torch.empty((L.MGP_PARTIALS,), dtype=f64).pin_memory()
         self._lib = lib
 
-    def launch(self, length_scale, noise: float) -> torch.Tensor:
-        """Enqueue one evaluation on the current stream; returns the device partials record."""
+    def launch(self, length_scale, noise: float, peers=None) -> torch.Tensor:
+        """Enqueue one evaluation on the current stream; returns the device partials record.
+        `peers` (a distributed.PeerChannel): the record is summed across the GPUs of the NVLink
+        domain inside the same kernel (`mgp_fused_loo_peers`)."""
         if self.x.device.index != torch.cuda.current_device():
             with torch.cuda.device(self.x.device):
-                return self.launch(length_scale, noise)
+                return self.launch(length_scale, noise, peers)
         ls = _ls_list(length_scale)
         for i, v in enumerate(ls):
             self.ls_host[i] = v
         self.p.length_scale_count = len(ls)
         self.p.noise = float(noise)
-        L.check(self._lib.mgp_fused_loo(C.byref(self.p), self.loss_id, self.boundary_scale,
-                                        _p(self.partials), _p(self.ws), self.ws_bytes, _stream()))
+        g = None if peers is None else C.byref(peers.group_struct())
+        L.check(self._lib.mgp_fused_loo_peers(C.byref(self.p), self.loss_id,
+                                              self.boundary_scale, _p(self.partials),
+                                              _p(self.ws), self.ws_bytes, g, _stream()))
         return self.partials
 
     def record(self, device_record: Optional[torch.Tensor] = None):
