@@ -109,18 +109,21 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                                               spec.heteroscedastic)
                   and x.data_ptr() % 16 == 0)
     if one_launch:
-        loo = ops.FusedLoo(x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
-                           loss_id=loss_fn.loss_id, boundary_scale=delta,
-                           partials=None if reducer is None else reducer.slot())
-        loo_scale = []  # lazily: a second evaluator for the noise quirk below
         # several GPUs: the kernel's own epilogue sums the records over NVLink peer memory
+        # (then, as on one GPU, its last block writes the result straight into pinned host
+        # memory); without peer access the record stays on the device for an all-reduce
         chan = None if reducer is None else reducer.channel()
         chan_scale = None if reducer is None else reducer.channel()
+        on_device = reducer is not None and chan is None
+        loo = ops.FusedLoo(x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
+                           loss_id=loss_fn.loss_id, boundary_scale=delta,
+                           partials=reducer.slot() if on_device else None)
+        loo_scale = []  # lazily: a second evaluator for the noise quirk below
 
-        def read(dev_rec, fused_sum):
-            if reducer is None:
-                return loo.record(dev_rec)
-            return reducer.to_host(dev_rec) if fused_sum else reducer.sum_to_host(dev_rec)
+        def read(ev, dev_rec, fused_sum):
+            if reducer is None or fused_sum:
+                return ev.record(dev_rec)
+            return reducer.sum_to_host(dev_rec)
 
         def obj_fn(*args, **theta):
             ls = spec.length_scale_arg(**theta)
@@ -131,11 +134,11 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                 if not loo_scale:
                     loo_scale.append(ops.FusedLoo(
                         x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
-                        loss_id=L.LOSS_NONE,
-                        partials=None if reducer is None else reducer.slot()))
-                rec_scale = read(loo_scale[0].launch(ls, model_noise, chan_scale),
+                        loss_id=L.LOSS_NONE, partials=reducer.slot() if on_device else None))
+                rec_scale = read(loo_scale[0], loo_scale[0].launch(ls, model_noise, chan_scale),
                                  chan_scale is not None)
-            rec = read(loo.launch(ls, spec.noise(theta.get("noise")), chan), chan is not None)
+            rec = read(loo, loo.launch(ls, spec.noise(theta.get("noise")), chan),
+                       chan is not None)
             return -finish(rec, rec_scale)
 
         return obj_fn

@@ -261,8 +261,12 @@ class FusedLoo:
             raise NotImplementedError("mgp_fused_loo handles one response (r == 1)")
         dev = self.x.device
         self.ls_host = (C.c_double * max(d, 1))()
-        self.partials = partials if partials is not None else torch.zeros(
-            (L.MGP_PARTIALS,), dtype=f64, device=dev)
+        # The record is written by the kernel's last block.  By default it lives in page-locked
+        # HOST memory (device-accessible under unified addressing): the 64 bytes cross the link
+        # as the kernel's own stores, no copy is enqueued and the host reads them as soon as
+        # the stream is synchronised.
+        self.pinned = torch.zeros((L.MGP_PARTIALS,), dtype=f64).pin_memory()
+        self.partials = partials if partials is not None else self.pinned
         self.p = L.MgpProblem(
             train_x=_p(self.x), query_x=_p(self.x), query_idx=_p(self.bi), nn_idx=_p(self.nn),
             train_y=_p(self.y), n=n, t=n, b=b, k=k, d=d, r=1, kernel_id=int(kernel_id),
@@ -273,8 +277,13 @@ class FusedLoo:
         self.ws = torch.zeros((self.ws_bytes,), dtype=torch.uint8, device=dev)  # counter = 0
         self.loss_id = int(loss_id)
         self.boundary_scale = float(boundary_scale)
-        self.pinned = torch.empty((L.MGP_PARTIALS,), dtype=f64).pin_memory()
         self._lib = lib
+        self._fn = lib.mgp_fused_loo_peers
+        self._pref = C.byref(self.p)
+        self._out = _p(self.partials)
+        self._ws = _p(self.ws)
+        self._np = self.pinned.numpy()
+        self._stream_obj = None
 
     def launch(self, length_scale, noise: float, peers=None) -> torch.Tensor:
         """Enqueue one evaluation on the current stream; returns the device partials record.
@@ -283,23 +292,29 @@ class FusedLoo:
         if self.x.device.index != torch.cuda.current_device():
             with torch.cuda.device(self.x.device):
                 return self.launch(length_scale, noise, peers)
-        ls = _ls_list(length_scale)
-        for i, v in enumerate(ls):
-            self.ls_host[i] = v
-        self.p.length_scale_count = len(ls)
+        if isinstance(length_scale, float):
+            self.ls_host[0] = length_scale
+            self.p.length_scale_count = 1
+        else:
+            ls = _ls_list(length_scale)
+            for i, v in enumerate(ls):
+                self.ls_host[i] = v
+            self.p.length_scale_count = len(ls)
         self.p.noise = float(noise)
         g = None if peers is None else C.byref(peers.group_struct())
-        L.check(self._lib.mgp_fused_loo_peers(C.byref(self.p), self.loss_id,
-                                              self.boundary_scale, _p(self.partials),
-                                              _p(self.ws), self.ws_bytes, g, _stream()))
+        rc = self._fn(self._pref, self.loss_id, self.boundary_scale, self._out, self._ws,
+                      self.ws_bytes, g, _stream())
+        if rc != 0:
+            L.check(rc)
         return self.partials
 
     def record(self, device_record: Optional[torch.Tensor] = None):
         """Host copy (numpy, 8 doubles) of the partials record after a stream synchronise."""
-        self.pinned.copy_(self.partials if device_record is None else device_record,
-                          non_blocking=True)
+        src = self.partials if device_record is None else device_record
+        if src is not self.pinned:
+            self.pinned.copy_(src, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.pinned.numpy().copy()
+        return self._np.copy()
 
 
 def fused_loo_supported(d: int, k: int, r: int, kernel_id: int, metric_id: int,
