@@ -273,6 +273,14 @@ size_t mgp_solve_workspace_bytes(int64_t b, int32_t k, int32_t r);
 int mgp_solve(const double* Kin, const double* Kcross, const double* Y, int64_t b, int32_t k,
               int32_t r, double kout, double* mean, double* var, double* yky, double* coeffs,
               int32_t* status, void* ws, size_t ws_bytes, void* stream);
+/* mask[i] = 1 when the labels of row i's neighbours are not all equal: the "nonconstant
+ * neighbourhood" filter of get_balanced_batch / full_filtered_batch
+ * (S/optimize/batch.py:58-64,104-110) and classify_any (S/examples/classify.py:577-583).
+ * `labels` is read with `label_stride` doubles between consecutive training rows (1 for a flat
+ * label array, class_count for column 0 of a one-hot matrix); the (b,k) gathered label tensor
+ * is never materialised. */
+int mgp_nn_label_mask(const double* labels, int64_t label_stride, const int64_t* nn_idx,
+                      int64_t b, int32_t k, uint8_t* mask, void* stream);
 /* einsum('ij,ijk->ik')  _muygps_fast_posterior_mean  S/_src/gp/muygps/numpy.py:70-77 */
 int mgp_rowdot(const double* Kcross, const double* coeffs, int64_t b, int32_t k, int32_t r,
                double* out, void* stream);

@@ -93,6 +93,7 @@ SIGNATURES = {
     "mgp_solve_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mgp_solve": (C.c_int, [_dp, _dp, _dp, _i64, _i32, _i32, _f64, _dp, _dp, _dp, _dp, _dp, _dp,
                             _sz, _dp]),
+    "mgp_nn_label_mask": (C.c_int, [_dp, _i64, _dp, _i64, _i32, _dp, _dp]),
     "mgp_rowdot": (C.c_int, [_dp, _dp, _i64, _i32, _i32, _dp, _dp]),
     "mgp_fp64_probe": (C.c_int, [_i32, _i32, _i32, _i32, _dp, _dp]),
 }

@@ -239,6 +239,44 @@ extern "C" int mgp_kernel_apply(int32_t kernel_id, const double* in, double pre_
   return check_launch("kernel_apply_kernel");
 }
 
+namespace mgp {
+// One warp per neighbourhood row: min / max of labels[nn_idx[row, :]] (column 0 of a strided
+// label array) -> 1 when the neighbourhood is NOT constant.  Replaces the (b,k) gather
+// `labels[nn_indices]` + two axis reductions of S/optimize/batch.py:58-64,104-110 and
+// S/examples/classify.py:577-583 without materialising the gathered labels.
+__global__ void nn_label_mask_kernel(const double* __restrict__ labels, long long stride,
+                                     const int64_t* __restrict__ nn_idx, long long b, int k,
+                                     uint8_t* __restrict__ mask) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= b) return;
+  double lo = INFINITY, hi = -INFINITY;
+  for (int j = lane; j < k; j += 32) {
+    const double v = labels[nn_idx[row * k + j] * stride];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) mask[row] = (hi != lo) ? 1 : 0;
+}
+}  // namespace mgp
+
+extern "C" int mgp_nn_label_mask(const double* labels, int64_t label_stride,
+                                 const int64_t* nn_idx, int64_t b, int32_t k, uint8_t* mask,
+                                 void* stream) {
+  using namespace mgp;
+  MGP_REQUIRE(b >= 0 && k >= 1 && label_stride >= 1, MGP_ERR_BAD_ARG, "bad sizes");
+  if (b == 0) return MGP_OK;
+  MGP_REQUIRE(labels && nn_idx && mask, MGP_ERR_BAD_ARG, "null pointer");
+  nn_label_mask_kernel<<<grid_for(b * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      labels, label_stride, nn_idx, b, k, mask);
+  return check_launch("nn_label_mask_kernel");
+}
+
 extern "C" int mgp_perturb(const double* Kin, int64_t b, int32_t k, double noise,
                            const double* noise_bk, double* out, void* stream) {
   MGP_REQUIRE(b >= 0 && k >= 1, MGP_ERR_BAD_ARG, "bad sizes");

@@ -622,6 +622,20 @@ def solve(Kin, Kcross=None, Y=None, kout=1.0, *, want_mean=False, want_var=False
 
 
 @_on_tensor_device
+def nn_label_mask(labels, nn_idx) -> torch.Tensor:
+    """bool (b,): the labels of row i's neighbours are not all equal.  `labels` is (n,) or a
+    one-hot style (n, class_count) matrix whose column 0 is inspected (classify.py:577-583)."""
+    lib = L.lib()
+    labels = fdev(labels, "labels")
+    nn_idx = idev(nn_idx, "nn_indices")
+    b, k = nn_idx.shape
+    stride = 1 if labels.dim() == 1 else labels.shape[1]
+    mask = torch.empty((b,), dtype=torch.uint8, device=labels.device)
+    L.check(lib.mgp_nn_label_mask(_p(labels), stride, _p(nn_idx), b, k, _p(mask), _stream()))
+    return mask.bool()
+
+
+@_on_tensor_device
 def rowdot(Kcross, coeffs) -> torch.Tensor:
     lib = L.lib()
     Kcross = fdev(Kcross, "Kcross")

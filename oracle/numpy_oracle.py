@@ -420,3 +420,36 @@ def loo_objective(
     if loss_id == LOSS_LOOPH:
         return -looph(mean, y_b, var, scale, **loss_kwargs), scale
     raise ValueError(f"unknown loss id {loss_id}")
+
+
+# ---- batch filters (S/optimize/batch.py, S/examples/classify.py) -------------------------
+def nonconstant_mask(labels, nn_indices):
+    """Rows whose neighbours do not all carry the same label.  S/optimize/batch.py:104-110
+    (1-D labels) and S/examples/classify.py:577-583 (column 0 of one-hot labels)."""
+    lab = np.asarray(labels)
+    col = lab if lab.ndim == 1 else lab[:, 0]
+    nn_labels = col[nn_indices]
+    return np.max(nn_labels, axis=1) != np.min(nn_labels, axis=1)
+
+
+def full_filtered_batch(train, labels, k):
+    """(batch_indices, batch_nn_indices).  S/optimize/batch.py:67-113."""
+    indices = np.arange(len(labels))
+    nn_indices, _ = knn_batch(train, indices, k)
+    mask = nonconstant_mask(labels, nn_indices)
+    return indices[mask], nn_indices[mask, :]
+
+
+def classify_any(kernel_id, metric_id, length_scale, noise, train_x, train_labels, test_x, k):
+    """Surrogate class scores.  S/examples/classify.py:536-608: rows whose neighbours agree
+    take the nearest neighbour's one-hot row, the others the posterior mean."""
+    nn, _ = knn_exact(train_x, test_x, k)
+    mask = nonconstant_mask(train_labels, nn)
+    pred = train_labels[nn[:, 0]].copy()
+    rows = np.where(mask)[0]
+    if len(rows):
+        Kin, Kcross = kernel_tensors(kernel_id, metric_id, length_scale, train_x, test_x, rows,
+                                     nn[rows])
+        pred[rows] = posterior_mean(homoscedastic_perturb(Kin, noise), Kcross,
+                                    train_labels[nn[rows]])
+    return pred
