@@ -84,6 +84,8 @@ class ModelSpec:
         if type(scale).__name__ == "DownSampleScale":
             raise NotImplementedError("DownSampleScale (stochastic) is not on the fused path")
         self.iteration_count = int(getattr(scale, "iteration_count", 1))
+        self._own_metric = self.metric_id
+        self._tensor_metric = None
 
     @staticmethod
     def of(muygps) -> "ModelSpec":
@@ -103,7 +105,27 @@ class ModelSpec:
 
     def length_scale_arg(self, **theta):
         ls = self.length_scales(**theta)
+        if self._tensor_metric is not None and self._tensor_metric != self._own_metric:
+            # MultivariateMuyGPS feeds every model the tensor of models[0]'s deformation; an
+            # isotropic model then applies ITS metric's length-scale rule (x / l for l2, x / l^2
+            # for F2; S/gp/deformation/metric.py:241,264) to the OTHER metric's tensor.  The
+            # same factor through the tensor metric's rule needs this effective length scale.
+            ell = ls[0]
+            factor = 1.0 / ell if self._own_metric == L.METRIC_L2 else 1.0 / (ell * ell)
+            return 1.0 / factor if self._tensor_metric == L.METRIC_L2 else factor ** -0.5
         return ls if self.anisotropic else ls[0]
+
+    def seen_through(self, tensor_metric_id: int) -> "ModelSpec":
+        """This model evaluated on distance tensors of another metric (see length_scale_arg)."""
+        import copy
+
+        if tensor_metric_id == self.metric_id or self.anisotropic:
+            return self
+        view = copy.copy(self)
+        view._own_metric = self.metric_id
+        view._tensor_metric = tensor_metric_id
+        view.metric_id = tensor_metric_id
+        return view
 
     def noise(self, override: Optional[float] = None):
         """Python float (homoscedastic / null) or a (b,k) tensor / array (heteroscedastic)."""

@@ -24,20 +24,31 @@ def tensors_from_indices(muygps, indices, nn_indices, test, train, targets, **kw
 
 
 def posterior_mean_from_indices(muygps, indices, nn_indices, test, train, targets, **kwargs):
+    if fused.is_multivariate(muygps):
+        return fused.mm_fused_regress(muygps, indices, nn_indices, test, train, targets,
+                                      want_var=False)
     return fused.fused_regress(muygps, indices, nn_indices, test, train, targets, want_var=False)
 
 
 def posterior_variance_from_indices(muygps, indices, nn_indices, test, train, targets, **kwargs):
+    if fused.is_multivariate(muygps):
+        return fused.mm_fused_regress(muygps, indices, nn_indices, test, train, targets,
+                                      want_mean=False)
     return fused.fused_regress(muygps, indices, nn_indices, test, train, targets,
                                want_mean=False)
 
 
 def regress_from_indices(muygps, indices, nn_indices, test, train, targets, **kwargs):
+    if fused.is_multivariate(muygps):
+        return fused.mm_fused_regress(muygps, indices, nn_indices, test, train, targets)
     return fused.fused_regress(muygps, indices, nn_indices, test, train, targets)
 
 
 def fast_posterior_mean_from_indices(muygps, indices, nn_indices, test_features,
                                      train_features, closest_index, coeffs_tensor):
+    if fused.is_multivariate(muygps):
+        return fused.mm_fast_posterior_mean(muygps, indices, nn_indices, test_features,
+                                            train_features, closest_index, coeffs_tensor)
     spec = ModelSpec.of(muygps)
     out = ops.fast_mean(
         fdev(train_features), fdev(test_features), idev(indices), idev(nn_indices),

@@ -111,3 +111,87 @@ def fused_optimize_scale(muygps, batch_indices, batch_nn_indices, train_features
         b, k = idev(batch_nn_indices).shape
         spec.set_scale(spec.sigma_from_mean_quadratic_form(float(out["yky"].sum()) / (b * k)))
     return muygps
+
+
+# ---- MultivariateMuyGPS (S/gp/multivariate_muygps.py:99-340): one model per response --------
+def is_multivariate(muygps) -> bool:
+    return hasattr(muygps, "models") and not hasattr(muygps, "kernel")
+
+
+def _column(targets, i):
+    t = fdev(targets)
+    return t[:, i].contiguous()
+
+
+def _model_specs(mmuygps):
+    """One spec per response, each seen through the tensors of models[0]'s deformation (the
+    reference builds ONE pairwise / crosswise tensor with models[0] and hands it to every
+    model's kernel, multivariate_muygps.py:136-139; from_indices.py:111-113)."""
+    specs = [ModelSpec.of(m) for m in mmuygps.models]
+    if len({s.anisotropic for s in specs}) != 1:
+        raise NotImplementedError("MultivariateMuyGPS mixing Isotropy and Anisotropy models")
+    return [s.seen_through(specs[0].metric_id) for s in specs]
+
+
+def mm_fused_regress(mmuygps, indices, nn_indices, test_features, train_features, train_targets,
+                     want_mean=True, want_var=True):
+    """(b,r) posterior means and (b,r) variances of r independent models over the SAME
+    neighbourhoods: one K1 launch per response on the shared index arrays.  Reproduces the
+    reference's variance quirk: `posterior_variance` already carries the model's scale and
+    MultivariateMuyGPS multiplies by it again (multivariate_muygps.py:183-192), i.e. scale^2."""
+    nn = idev(nn_indices)
+    idx = None if indices is None else idev(indices)
+    x = fdev(train_features)
+    q = x if test_features is None else fdev(test_features)
+    means, variances = [], []
+    for i, spec in enumerate(_model_specs(mmuygps)):
+        out = fused_call(spec, idx, nn, q, x, _column(train_targets, i), scale=spec.scale() ** 2,
+                         want_mean=want_mean, want_var=want_var)
+        if want_mean:
+            means.append(out["mean"][:, 0])
+        if want_var:
+            variances.append(out["var"])
+    host = (indices, nn_indices, test_features, train_features, train_targets)
+    res = []
+    if want_mean:
+        res.append(like_input(torch.stack(means, dim=1), *host))
+    if want_var:
+        res.append(like_input(torch.stack(variances, dim=1), *host))
+    return tuple(res) if len(res) > 1 else res[0]
+
+
+def mm_fused_fast_coefficients(mmuygps, nn_indices_fast, train_features, train_targets):
+    """(n,k,r) fast-mean coefficients, one K3 launch per response.  The reference perturbs Kin
+    before handing it to `fast_coefficients`, which perturbs again
+    (multivariate_muygps.py:224-231): the nugget enters twice, and so it does here.  (The
+    reference then DISCARDS each column -- `mm.assign` returns a copy that is never bound -- and
+    returns zeros; we return the columns it computed.)"""
+    cols = []
+    for i, spec in enumerate(_model_specs(mmuygps)):
+        noise = spec.noise(None)
+        theta = {} if spec.heteroscedastic else {"noise": 2.0 * noise}
+        if spec.heteroscedastic:
+            raise NotImplementedError("multivariate fast coefficients with heteroscedastic noise")
+        out = fused_call(spec, None, nn_indices_fast, train_features, train_features,
+                         _column(train_targets, i), theta=theta, want_mean=False,
+                         want_var=False, want_coeffs=True)["coeffs"]
+        cols.append(out[:, :, 0])
+    return like_input(torch.stack(cols, dim=2), nn_indices_fast, train_features, train_targets)
+
+
+def mm_fast_posterior_mean(mmuygps, indices, nn_indices, test_features, train_features,
+                           closest_index, coeffs_tensor):
+    """_mmuygps_fast_posterior_mean (S/_src/gp/muygps/numpy.py:80-85): per response, the
+    crosswise covariances of ITS kernel dotted with its coefficient column.  (As with the
+    coefficients, the reference's wrapper never binds the `mm.assign` results and feeds zeros
+    to this einsum, multivariate_muygps.py:262-270; we compute what it defines.)"""
+    coeffs = fdev(coeffs_tensor)
+    cols = []
+    for i, spec in enumerate(_model_specs(mmuygps)):
+        out = ops.fast_mean(fdev(train_features), fdev(test_features), idev(indices),
+                            idev(nn_indices), idev(closest_index),
+                            coeffs[:, :, i].contiguous(), kernel_id=spec.kernel_id,
+                            metric_id=spec.metric_id, length_scale=spec.length_scale_arg())
+        cols.append(out[:, 0])
+    return like_input(torch.stack(cols, dim=1), indices, nn_indices, test_features,
+                      train_features, coeffs_tensor)

@@ -1,3 +1,3 @@
 """`muygpys_b200.gp` mirrors the import layout of `MuyGPyS.gp` (S/gp/__init__.py)."""
 
-from ..model import MuyGPS  # noqa: F401
+from ..model import MultivariateMuyGPS, MuyGPS  # noqa: F401

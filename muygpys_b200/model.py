@@ -166,3 +166,62 @@ class MuyGPS:
                              train_targets):
         return fused.fused_optimize_scale(self, batch_indices, batch_nn_indices, train_features,
                                           train_targets)
+
+
+class MultivariateMuyGPS:
+    """One MuyGPS per response over shared neighbourhoods (S/gp/multivariate_muygps.py:28-340).
+
+    Built like the reference's: `MultivariateMuyGPS(*model_args)` with one keyword dictionary
+    per response.  The `*_from_indices` entry points and `fused_*` methods run one fused launch
+    per response on the shared index arrays; the staged methods keep the reference's
+    (pairwise_diffs, crosswise_diffs, ...) signatures."""
+
+    def __init__(self, *model_args):
+        self.models = [MuyGPS(**args) for args in model_args]
+
+    def fixed(self) -> bool:
+        return all(model.fixed() for model in self.models)
+
+    def make_predict_tensors(self, *args, **kwargs):
+        return self.models[0].make_predict_tensors(*args, **kwargs)
+
+    def make_train_tensors(self, *args, **kwargs):
+        return self.models[0].make_train_tensors(*args, **kwargs)
+
+    def posterior_mean(self, pairwise_diffs, crosswise_diffs, batch_nn_targets):
+        y = fdev(batch_nn_targets)
+        cols = [fdev(m.posterior_mean(m.kernel(pairwise_diffs), m.kernel(crosswise_diffs),
+                                      y[:, :, i].contiguous()))
+                for i, m in enumerate(self.models)]
+        return like_input(torch.stack(cols, dim=1), pairwise_diffs, crosswise_diffs,
+                          batch_nn_targets)
+
+    def posterior_variance(self, pairwise_diffs, crosswise_diffs):
+        # scale enters twice, as in the reference (multivariate_muygps.py:183-192)
+        cols = [fdev(m.posterior_variance(m.kernel(pairwise_diffs), m.kernel(crosswise_diffs)))
+                * m.scale() for m in self.models]
+        return like_input(torch.stack(cols, dim=1), pairwise_diffs, crosswise_diffs)
+
+    def fast_coefficients(self, pairwise_diffs_fast, train_nn_targets_fast):
+        y = fdev(train_nn_targets_fast)
+        # the nugget enters twice, as in the reference (multivariate_muygps.py:224-231)
+        cols = [fdev(m.fast_coefficients(m.noise.perturb(m.kernel(pairwise_diffs_fast)),
+                                         y[:, :, i].contiguous()))
+                for i, m in enumerate(self.models)]
+        return like_input(torch.stack(cols, dim=2), pairwise_diffs_fast, train_nn_targets_fast)
+
+    def fast_posterior_mean(self, crosswise_diffs, coeffs_tensor):
+        c = fdev(coeffs_tensor)
+        cols = [ops.rowdot(fdev(m.kernel(crosswise_diffs)), c[:, :, i].contiguous())[:, 0]
+                for i, m in enumerate(self.models)]
+        return like_input(torch.stack(cols, dim=1), crosswise_diffs, coeffs_tensor)
+
+    # fused (indices in)
+    def fused_regress(self, indices, nn_indices, test_features, train_features, train_targets,
+                      want_mean=True, want_var=True):
+        return fused.mm_fused_regress(self, indices, nn_indices, test_features, train_features,
+                                      train_targets, want_mean=want_mean, want_var=want_var)
+
+    def fused_fast_coefficients(self, nn_indices_fast, train_features, train_targets):
+        return fused.mm_fused_fast_coefficients(self, nn_indices_fast, train_features,
+                                                train_targets)

@@ -156,3 +156,92 @@ def test_fused_entry_points_take_genuine_reference_objects(name):
     assert type(got_opt) is MuyGPS
     np.testing.assert_allclose(got_opt.get_opt_params()[1], want_opt.get_opt_params()[1],
                                rtol=5e-3)
+
+
+def test_multivariate_fused_path_matches_reference_mmuygps():
+    """MultivariateMuyGPS (S/gp/multivariate_muygps.py:99-340): r models over shared
+    neighbourhoods.  Our fused entry points take the GENUINE reference object (and the mirror
+    class built from the same dictionaries) and must reproduce the reference's numbers,
+    including its quirks (scale applied twice to the variance, nugget applied twice to the fast
+    coefficients)."""
+    from MuyGPyS.examples import from_indices as ref_api
+    from MuyGPyS.gp import MultivariateMuyGPS as RefMM
+    from MuyGPyS.gp.deformation import F2, Isotropy, l2
+    from MuyGPyS.gp.hyperparameter import FixedScale, Parameter
+    from MuyGPyS.gp.kernels import RBF, Matern
+    from MuyGPyS.gp.noise import HomoscedasticNoise
+    from MuyGPyS.gp.tensors import fast_nn_update, make_fast_predict_tensors
+    from MuyGPyS.neighbors import NN_Wrapper
+
+    import muygpys_b200.gp as G
+    import muygpys_b200.gp.deformation as GD
+    import muygpys_b200.gp.hyperparameter as GH
+    import muygpys_b200.gp.kernels as GK
+    import muygpys_b200.gp.noise as GN
+    from muygpys_b200 import fused
+    from muygpys_b200.examples import from_indices as our_api
+
+    rng = np.random.default_rng(21)
+    n, t, k = 1500, 200, 20
+    x = rng.uniform(size=(n, 3))
+    q = rng.uniform(size=(t, 3))
+    y = np.stack([np.sin(3 * x[:, 0]) + x[:, 1], np.cos(2 * x[:, 2]) * x[:, 0]], axis=1)
+    y += 0.05 * rng.normal(size=y.shape)
+
+    def args(M, D, N, H, kernels, deform, metric_l2, metric_f2):
+        s1, s2 = H.FixedScale(), H.FixedScale()
+        s1._set(1.7)
+        s2._set(0.6)
+        return [
+            {"kernel": kernels.Matern(smoothness=H.Parameter(1.5),
+                                      deformation=deform.Isotropy(metric_l2, H.Parameter(0.4))),
+             "noise": N.HomoscedasticNoise(1e-3), "scale": s1},
+            {"kernel": kernels.RBF(deformation=deform.Isotropy(metric_f2, H.Parameter(0.7))),
+             "noise": N.HomoscedasticNoise(2e-3), "scale": s2},
+        ]
+
+    import MuyGPyS.gp.deformation as RD
+    import MuyGPyS.gp.hyperparameter as RH
+    import MuyGPyS.gp.kernels as RK
+    import MuyGPyS.gp.noise as RN
+
+    ref = RefMM(*args(None, None, RN, RH, RK, RD, l2, F2))
+    mirror = G.MultivariateMuyGPS(*args(None, None, GN, GH, GK, GD, GD.l2, GD.F2))
+    nbrs = NN_Wrapper(x, k, nn_method="exact", algorithm="ball_tree")
+    nn, _ = nbrs.get_nns(q)
+    t_idx = np.arange(t)
+    want_mean, want_var = ref_api.regress_from_indices(ref, t_idx, nn, q, x, y)
+    for model in (ref, mirror):
+        assert fused.is_multivariate(model)
+        got_mean, got_var = our_api.regress_from_indices(model, t_idx, nn, q, x, y)
+        assert got_mean.shape == (t, 2) and got_var.shape == (t, 2)
+        assert_close(got_mean, want_mean, 1e-10, "multivariate mean")
+        assert_close(got_var, want_var, 1e-10, "multivariate variance")
+    # fast path: coefficients of every training point, then a k-dot per test point
+    train_nn, _ = nbrs.get_batch_nns(np.arange(n))
+    nn_fast = fast_nn_update(train_nn)
+    pw_fast, y_fast = make_fast_predict_tensors(train_nn, x, y)  # differences (n,k,k,d)
+    # The reference's MultivariateMuyGPS.fast_coefficients discards the result of `mm.assign`
+    # (multivariate_muygps.py:222-231; numpy's assign copies), so it returns ZEROS.  The values
+    # it computes on the way -- each model's coefficients with the nugget applied twice -- are
+    # the definition we reproduce.
+    assert not np.any(ref.fast_coefficients(l2(pw_fast), y_fast))
+    want_coeffs = np.stack(
+        [m.fast_coefficients(m.noise.perturb(m.kernel(l2(pw_fast))), y_fast[:, :, i])
+         for i, m in enumerate(ref.models)], axis=2)
+    got_coeffs = fused.mm_fused_fast_coefficients(ref, nn_fast, x, y)
+    assert_close(got_coeffs, want_coeffs, 1e-9, "multivariate fast coefficients")
+    closest = nn[:, 0]
+    # same defect in MultivariateMuyGPS.fast_posterior_mean (:262-270): Kcross stays zero
+    assert not np.any(ref_api.fast_posterior_mean_from_indices(
+        ref, t_idx, nn_fast[closest], q, x, closest, want_coeffs))
+    cw_fast = ref.models[0].kernel.deformation.crosswise_tensor(q, x, t_idx, nn_fast[closest])
+    want_fast = np.stack([np.einsum("bj,bj->b", m.kernel(cw_fast), want_coeffs[closest][:, :, i])
+                          for i, m in enumerate(ref.models)], axis=1)
+    got_fast = our_api.fast_posterior_mean_from_indices(ref, t_idx, nn_fast[closest], q, x,
+                                                        closest, want_coeffs)
+    assert_close(got_fast, want_fast, 1e-10, "multivariate fast mean")
+    # the mirror object's staged methods (materialised tensors) follow the same definitions
+    cw, pw, nn_t = mirror.make_predict_tensors(t_idx, nn, q, x, y)
+    assert_close(mirror.posterior_mean(pw, cw, nn_t), want_mean, 1e-10, "staged mv mean")
+    assert_close(mirror.posterior_variance(pw, cw), want_var, 1e-10, "staged mv variance")
