@@ -34,6 +34,8 @@ extern "C" {
 #define MGP_MAX_ANISO_DIM 32 /* anisotropic length scales live in kernel params */
 #define MGP_PARTIALS 8       /* doubles in a loss/scale partials record */
 #define MGP_MAX_PEERS 8      /* GPUs of one NVLink domain that can share a partials record */
+#define MGP_GRAD_PARAMS 4    /* gradient slots: length scales of features 0..2, then the nugget */
+#define MGP_GRAD_DOUBLES 20  /* 5 sums per gradient slot, see mgp_fused_loo_grad */
 
 typedef enum mgp_status {
   MGP_OK = 0,
@@ -187,6 +189,24 @@ int mgp_peer_sum8(double* partials, const mgp_peer_group* g, void* stream);
 int mgp_fused_loo_peers(const mgp_problem* p, int32_t loss_id, double boundary_scale,
                         double* partials, void* ws, size_t ws_bytes, const mgp_peer_group* g,
                         void* stream);
+
+/* The same launch with the ANALYTIC GRADIENT of the objective's ingredients (SURVEY.md 8f-2;
+ * the reference finite-differences, S/_src/optimize/chassis/numpy.py:68-74).  After the
+ * factorisation the kernel back-substitutes w = K^-1 kcross and alpha = K^-1 y on the stored
+ * factor and re-evaluates dK/dtheta entry by entry (never stored):
+ *   d mean = dc^T alpha - w^T dK alpha,  d var = -2 dc^T w + w^T dK w,  d yky = -alpha^T dK alpha
+ * for theta = the length scale of feature 0, 1, 2 (slots 0..2; an isotropic model's derivative
+ * is the sum over its features) and the nugget tau^2 (slot 3).  `grad` (MGP_GRAD_DOUBLES doubles,
+ * device or pinned host) receives, per slot t, the batch sums
+ *   grad[5t+0] = sum 2 e dm        (e = mean - target)      -> d sum e^2           (mse)
+ *   grad[5t+1] = sum 2 e dm / v    grad[5t+2] = sum e^2 dv / v^2    grad[5t+3] = sum dv / v
+ *   grad[5t+4] = sum d yky                                   -> d sigma^2 (analytic scale)
+ * from which the host finishes d mse and d lool (muygpys_b200/objective.py).  grad == NULL is
+ * mgp_fused_loo_peers.  The gradient sums are per rank: `partials` goes through the peer
+ * exchange, `grad` is summed across ranks by the caller. */
+int mgp_fused_loo_grad(const mgp_problem* p, int32_t loss_id, double boundary_scale,
+                       double* partials, double* grad, void* ws, size_t ws_bytes,
+                       const mgp_peer_group* g, void* stream);
 
 /* ---- losses and scale partials (a14/a15) -------------------------------
  * Accumulates (adds) a partials record over b rows into `partials`

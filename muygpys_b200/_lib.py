@@ -23,6 +23,8 @@ MGP_ERR_CUDA = -3
 MGP_ERR_WORKSPACE = -4
 MGP_PARTIALS = 8
 MGP_MAX_PEERS = 8
+MGP_GRAD_PARAMS = 4
+MGP_GRAD_DOUBLES = 20
 MGP_MAX_ANISO_DIM = 32
 
 # enums (mgp_kernel_id, mgp_metric_id, mgp_loss_id, partial slots)
@@ -74,6 +76,7 @@ SIGNATURES = {
     "mgp_peer_buffer_bytes": (_sz, []),
     "mgp_peer_sum8": (C.c_int, [_dp, _PG, _dp]),
     "mgp_fused_loo_peers": (C.c_int, [_PP, _i32, _f64, _dp, _dp, _sz, _PG, _dp]),
+    "mgp_fused_loo_grad": (C.c_int, [_PP, _i32, _f64, _dp, _dp, _dp, _sz, _PG, _dp]),
     "mgp_loss_workspace_bytes": (_sz, [_i64, _i32]),
     "mgp_loss_partials": (C.c_int, [_i32, _dp, _dp, _dp, _dp, _dp, _f64, _i64, _i32, _dp, _dp,
                                     _sz, _dp]),

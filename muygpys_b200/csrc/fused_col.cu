@@ -9,6 +9,10 @@ int launch_fused_col_f0(const mgp_problem*, const Model&, const ColLoo&, int*, c
 int launch_fused_col_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_col_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_col_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_colg_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_colg_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_colg_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_colg_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 
 int fused_variant();
 int validate_problem(const mgp_problem* p);
@@ -38,6 +42,17 @@ int fused_col_supported(const mgp_problem* p, const Model& model) {
 
 static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& loo, int* grid_out,
                       cudaStream_t stream) {
+  if (loo.grad != nullptr) {
+    switch (col_formula(model)) {
+      case F_M05: return launch_fused_colg_f0(p, model, loo, grid_out, stream);
+      case F_M15: return launch_fused_colg_f1(p, model, loo, grid_out, stream);
+      case F_M25: return launch_fused_colg_f2(p, model, loo, grid_out, stream);
+      case F_GAUSS: return launch_fused_colg_f3(p, model, loo, grid_out, stream);
+      default:
+        set_error("column kernel does not support this kernel / metric pair");
+        return MGP_ERR_UNSUPPORTED;
+    }
+  }
   switch (col_formula(model)) {
     case F_M05: return launch_fused_col_f0(p, model, loo, grid_out, stream);
     case F_M15: return launch_fused_col_f1(p, model, loo, grid_out, stream);
@@ -57,7 +72,7 @@ int launch_fused_col(const mgp_problem* p, const Model& model, cudaStream_t stre
 // workspace of mgp_fused_loo: [counter (256 B)] [per-warp records] -- the record area is sized for
 // the largest grid any device of this process can run (4 CTAs per SM)
 static size_t loo_ws_bytes() {
-  return 256 + (size_t)sm_count() * 4 * COL_WARPS * MGP_PARTIALS * sizeof(double);
+  return 256 + (size_t)sm_count() * 4 * COL_NREC_GRAD * sizeof(double);
 }
 
 }  // namespace mgp
@@ -111,6 +126,13 @@ extern "C" int mgp_fused_loo(const mgp_problem* p, int32_t loss_id, double bound
 extern "C" int mgp_fused_loo_peers(const mgp_problem* p, int32_t loss_id, double boundary_scale,
                                    double* partials, void* ws, size_t ws_bytes,
                                    const mgp_peer_group* g, void* stream) {
+  return mgp_fused_loo_grad(p, loss_id, boundary_scale, partials, nullptr, ws, ws_bytes, g,
+                            stream);
+}
+
+extern "C" int mgp_fused_loo_grad(const mgp_problem* p, int32_t loss_id, double boundary_scale,
+                                  double* partials, double* grad, void* ws, size_t ws_bytes,
+                                  const mgp_peer_group* g, void* stream) {
   using namespace mgp;
   int rc = validate_problem(p);
   if (rc != MGP_OK) return rc;
@@ -145,6 +167,12 @@ extern "C" int mgp_fused_loo_peers(const mgp_problem* p, int32_t loss_id, double
   loo.counter = (unsigned int*)ws;
   loo.warp_rec = (double*)((char*)ws + 256);
   loo.partials = partials;
+  loo.grad = grad;
+  if (grad != nullptr) {
+    // 1 / l_f as the deformation applies it (isotropic: the same value for every feature)
+    for (int f = 0; f < p->d && f < 3; ++f)
+      loo.inv_len[f] = 1.0 / p->length_scale[p->length_scale_count == 1 ? 0 : f];
+  }
   loo.loss_id = loss_id;
   loo.boundary_scale = boundary_scale > 0.0 ? boundary_scale : 1.0;
   int grid = 0;  // the full persistent grid, whatever the batch size (fixed summation order)

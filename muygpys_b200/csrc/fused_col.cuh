@@ -42,8 +42,10 @@ namespace mgp {
 
 // Optional fused epilogue: leave-one-out loss / scale partials of the batch (a14-a16).
 struct ColLoo {
-  double* warp_rec;        // (grid * COL_WARPS, MGP_PARTIALS) per-warp partial records, or NULL
+  double* warp_rec;        // (grid, record length) per-block partial records, or NULL
   double* partials;        // (MGP_PARTIALS) final record, written by the last CTA
+  double* grad;            // (MGP_GRAD_DOUBLES) gradient sums (gradient kernels only)
+  double inv_len[3];       // 1 / l_f of the features (gradient kernels only)
   unsigned int* counter;   // arrival counter (self-resetting)
   int loss_id;
   double boundary_scale;
@@ -62,7 +64,10 @@ constexpr int COL_MAX_T = 8;
 // ptxas follows source order locally (the first version of this kernel called a scalar
 // routine twice per tile and got two back-to-back serial chains, `wait` stalls on every DFMA of
 // the polynomial).  Here every dependency level offers N independent instructions.
-template <int F, int N>
+// MODE 0: the covariance.  MODE 1: phi = -K'(s) / s, the factor of the length-scale derivative
+// dK/dl_f = phi z_f^2 / l_f (z = prescaled coordinate differences, s = |z|): e^-s / s (M1/2),
+// e^-s (M3/2), (1 + s) e^-s / 3 (M5/2), e^(-u/2) (Gaussian).
+template <int F, int N, int MODE = 0>
 __device__ __forceinline__ void cov_n(const double (&u2)[N], double tab64, double (&out)[N]) {
 #ifdef MGP_DBG_NOEVAL
 #pragma unroll
@@ -72,6 +77,7 @@ __device__ __forceinline__ void cov_n(const double (&u2)[N], double tab64, doubl
   const double LOG2E = 1.4426950408889634;
   const double MAGIC = 211106232532992.0;  // 1.5 * 2^47: ulp = 2^-5
   double s[N];
+  double rinv[N];  // 1 / s (MODE 1, M1/2 only)
   if (F == F_GAUSS) {
 #pragma unroll
     for (int i = 0; i < N; ++i) s[i] = 0.5 * u2[i];
@@ -89,6 +95,11 @@ __device__ __forceinline__ void cov_n(const double (&u2)[N], double tab64, doubl
     for (int i = 0; i < N; ++i) v[i] = e[i] * v[i];
 #pragma unroll
     for (int i = 0; i < N; ++i) s[i] = fma(g[i], v[i], g[i]);
+    if (MODE == 1 && F == F_M05) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        rinv[i] = (__double2hiint(u2[i]) > 0x03c00000) ? fma(r[i], v[i], r[i]) : 0.0;
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) s[i] = (__double2hiint(u2[i]) > 0x03c00000) ? s[i] : 0.0;
   }
@@ -124,6 +135,15 @@ __device__ __forceinline__ void cov_n(const double (&u2)[N], double tab64, doubl
     const double sc = __hiloint2double(__double2hiint(p[i]) + ((ki[i] >> 5) << 20),
                                        __double2loint(p[i]));
     p[i] = (__double2hiint(s[i]) < 0x4085e000) ? sc : 0.0;  // s < 700
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (F == F_M05) out[i] = p[i] * rinv[i];
+      else if (F == F_M25) out[i] = fma(s[i], 1.0 / 3.0, 1.0 / 3.0) * p[i];
+      else out[i] = p[i];  // M3/2: e^-s; Gaussian: e^(-u/2)
+    }
+    return;
   }
   if (F == F_M15) {
 #pragma unroll
@@ -177,20 +197,30 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __host__ __device__ constexpr int lslot(int I, int P) { return I * (I - 1) / 2 + P; }
 
 // per-warp shared memory in doubles
-static inline size_t col_warp_doubles(int T, int k, int d) {
+static inline size_t col_warp_doubles(int T, int k, int d, bool grad = false) {
   const size_t L = (size_t)(T * (T - 1) / 2) * 64;
   const size_t dinv = 8 * (size_t)T;
   const size_t pts = (size_t)((((k + 1) * d) + 1) & ~1);
   const size_t ys = (size_t)((k + 2) & ~1);
-  return L + dinv + 2 * pts + 2 * ys;
+  // gradient kernels keep M_J of every tile column, the last two diagonal tiles and the
+  // solution vectors w = K^-1 kcross, alpha = K^-1 y
+  const size_t g = grad ? (size_t)(T + 2) * 64 + 16 * (size_t)T : 0;
+  return L + dinv + 2 * pts + 2 * ys + g;
 }
 
-template <int T, int F, int D>
-__global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
+constexpr int COL_NREC_GRAD = 32;  // MGP_PARTIALS + MGP_GRAD_DOUBLES, padded
+
+template <int T, int F, int D, bool GRAD = false>
+__global__ void __launch_bounds__(COL_WARPS * 32, GRAD ? 3 : MGP_COL_MINB)
     fused_col_kernel(const TileArgs a, const ColLoo loo, int pts_doubles, int ys_doubles,
                      int warp_doubles) {
   extern __shared__ double smem[];
   constexpr int NL = T * (T - 1) / 2;
+  constexpr int NREC = GRAD ? COL_NREC_GRAD : MGP_PARTIALS;
+  // per-warp loss / scale (/ gradient) sums, updated by lane 0 once per neighbourhood
+  __shared__ double s_acc[COL_WARPS][NREC];
+  for (int e = threadIdx.x; e < COL_WARPS * NREC; e += blockDim.x) (&s_acc[0][0])[e] = 0.0;
+  __syncthreads();
   constexpr int W = 8 * (T - 1);  // columns left of the last diagonal tile
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rho = lane >> 2, q = lane & 3, qb = lane & ~3;
@@ -203,6 +233,10 @@ __global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
   double* dinv_s = Ls + NL * 64;                    // -1/d per eliminated column
   double* pts_buf = dinv_s + 8 * T;                 // 2 x (k+1) points, point k = query
   double* ys_buf = pts_buf + 2 * pts_doubles;       // 2 x k targets
+  double* Ms = ys_buf + 2 * ys_doubles;             // GRAD: M_J = L_JJ^-T per tile column
+  double* Dg = Ms + T * 64;                         // GRAD: final diagonal tiles T-2, T-1
+  double* wv = Dg + 2 * 64;                         // GRAD: w = K^-1 kcross (8 T entries)
+  double* av = wv + 8 * T;                          // GRAD: alpha = K^-1 y
 
   const long long wglobal = (long long)blockIdx.x * COL_WARPS + warp;
   const long long wstride = (long long)gridDim.x * COL_WARPS;
@@ -235,10 +269,6 @@ __global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
   cp_async_commit();
   s0 = load_src(wglobal + wstride, lane);
   s1 = load_src(wglobal + wstride, lane + 32);
-
-  // per-warp loss / scale partials (lane 0)
-  double acc_sq = 0.0, acc_yky = 0.0, acc_sqv = 0.0, acc_logv = 0.0, acc_aux = 0.0;
-  int acc_rows = 0, acc_bad = 0;
 
   int buf = 0;
   for (long long row = wglobal; row < a.b; row += wstride, buf ^= 1) {
@@ -472,6 +502,12 @@ __global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
         if ((j & 1) == 0) work_item(j >> 1);
       }
       if (rho == 0) *reinterpret_cast<double2*>(dinv_s + 8 * J + 2 * q) = make_double2(-di0, -di1);
+      if (GRAD) {
+        *reinterpret_cast<double2*>(Ms + J * 64 + 2 * lane) = make_double2(v0, v1);
+        if (J >= T - 2)
+          *reinterpret_cast<double2*>(Dg + (J - (T - 2)) * 64 + 2 * lane) =
+              make_double2(c[J][0], c[J][1]);
+      }
       // ---- outputs from the Schur complement ---------------------------------------------
       if (J == T - 1) {
         if (kl < 7) {
@@ -509,6 +545,171 @@ __global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
       __syncwarp();  // dinv_s of this column is read by every lane from the next column on
     }
 
+    // ---- gradient of (mean, variance, y^T K^-1 y) w.r.t. length scale(s) and nugget ---------
+    // d mean = dc^T alpha - w^T dK alpha, d var = -2 dc^T w + w^T dK w, d yky = -alpha^T dK alpha
+    // with w = K^-1 kcross, alpha = K^-1 y from a back substitution on the stored factor, and
+    // dK_ij / dl_f = phi(s_ij) z_f^2 / l_f re-evaluated entry by entry (never stored).
+    double gdm[4] = {0.0, 0.0, 0.0, 0.0}, gdv[4] = {0.0, 0.0, 0.0, 0.0},
+           gdy[4] = {0.0, 0.0, 0.0, 0.0};
+    if (GRAD) {
+      const int Jlast = (k - 1) >> 3;           // last tile column that holds K columns
+      const int Rk = k >> 3, Ry = (k + 1) >> 3;  // tile rows of the cross row and the target row
+      const int ly = (k + 1) & 7;
+      for (int e = lane; e < 8 * T; e += 32) {
+        wv[e] = 0.0;
+        av[e] = 0.0;
+      }
+      __syncwarp();
+      double xw[T], xa[T];  // this lane's row (rho) of the solution blocks
+#pragma unroll
+      for (int I = 0; I < T; ++I) xw[I] = xa[I] = 0.0;
+      // tile (row tile R, column tile J) as stored: finished tile, or final diagonal tile
+      auto stored = [&](int R, int J2, int off) -> double2 {
+        const double* base = (J2 < R) ? Ls + lslot(R, J2) * 64 : Dg + (R - (T - 2)) * 64;
+        return *reinterpret_cast<const double2*>(base + off);
+      };
+#pragma unroll
+      for (int J = T - 1; J >= 0; --J) {
+        if (J <= Jlast) {
+          const int nc = min(8, k - 8 * J);  // eliminated columns of this tile column
+          // t = z - sum_{I > J} U[I][J]^T x_I, z = rows k / k+1 of U (= L^-1 kcross, L^-1 y)
+          double ac0 = 0.0, ac1 = 0.0, ay0 = 0.0, ay1 = 0.0;
+#pragma unroll
+          for (int I = J + 1; I < T; ++I) {
+            if (I <= Jlast) {
+              const double2 u =
+                  *reinterpret_cast<const double2*>(Ls + lslot(I, J) * 64 + 2 * lane);
+              ac0 = fma(u.x, xw[I], ac0);
+              ac1 = fma(u.y, xw[I], ac1);
+              ay0 = fma(u.x, xa[I], ay0);
+              ay1 = fma(u.y, xa[I], ay1);
+            }
+          }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {  // sum over the 8 rows (lanes with the same q)
+            ac0 += __shfl_xor_sync(0xffffffffu, ac0, o);
+            ac1 += __shfl_xor_sync(0xffffffffu, ac1, o);
+            ay0 += __shfl_xor_sync(0xffffffffu, ay0, o);
+            ay1 += __shfl_xor_sync(0xffffffffu, ay1, o);
+          }
+          const double2 zc = (J <= Rk) ? stored(Rk, J, kl * 8 + 2 * q) : make_double2(0.0, 0.0);
+          const double2 zy = stored(Ry, J, ly * 8 + 2 * q);
+          const double2 nd = *reinterpret_cast<const double2*>(dinv_s + 8 * J + 2 * q);
+          const bool in0 = 2 * q < nc, in1 = 2 * q + 1 < nc;
+          const double sc0 = in0 ? (ac0 - zc.x) * nd.x : 0.0, sc1 = in1 ? (ac1 - zc.y) * nd.y : 0.0;
+          const double sy0 = in0 ? (ay0 - zy.x) * nd.x : 0.0, sy1 = in1 ? (ay1 - zy.y) * nd.y : 0.0;
+          // x_J = L_JJ^-T D^-1 t = M_J (D^-1 t): row rho, summed over the quad
+          const double2 m = *reinterpret_cast<const double2*>(Ms + J * 64 + 2 * lane);
+          double vw = fma(m.x, sc0, m.y * sc1), va = fma(m.x, sy0, m.y * sy1);
+          vw += __shfl_xor_sync(0xffffffffu, vw, 1);
+          va += __shfl_xor_sync(0xffffffffu, va, 1);
+          vw += __shfl_xor_sync(0xffffffffu, vw, 2);
+          va += __shfl_xor_sync(0xffffffffu, va, 2);
+          xw[J] = (rho < nc) ? vw : 0.0;
+          xa[J] = (rho < nc) ? va : 0.0;
+          if (q == 0) {
+            wv[8 * J + rho] = xw[J];
+            av[8 * J + rho] = xa[J];
+          }
+        }
+      }
+      __syncwarp();
+      // weighted re-evaluation: per tile row I the row-factored sums
+      //   Ra_f = sum_j phi z_f^2 alpha_j,  Rw_f = sum_j phi z_f^2 w_j   (j over tile columns <= I)
+      // fold into  w^T dK alpha, w^T dK w, alpha^T dK alpha  (diagonal tiles count pairs twice)
+      double Gm[D], Gv[D], Gy[D];
+#pragma unroll
+      for (int f = 0; f < D; ++f) Gm[f] = Gv[f] = Gy[f] = 0.0;
+#pragma unroll
+      for (int I = 0; I < T; ++I) {
+        if (I <= Jlast) {
+          const Pt<D> pr = ld_pt<D>(pts, min(8 * I + rho, k));
+          double Ra[D], Rw[D];
+#pragma unroll
+          for (int f = 0; f < D; ++f) Ra[f] = Rw[f] = 0.0;
+          auto tile_pair = [&](int Ja, int Jb, bool two) {
+            const Pt<D> a0 = ld_pt<D>(pts, min(8 * Ja + 2 * q, k)),
+                        a1 = ld_pt<D>(pts, min(8 * Ja + 2 * q + 1, k));
+            const Pt<D> b0 = ld_pt<D>(pts, min(8 * Jb + 2 * q, k)),
+                        b1 = ld_pt<D>(pts, min(8 * Jb + 2 * q + 1, k));
+            const double2 wa = *reinterpret_cast<const double2*>(wv + 8 * Ja + 2 * q);
+            const double2 aa = *reinterpret_cast<const double2*>(av + 8 * Ja + 2 * q);
+            const double2 wb = *reinterpret_cast<const double2*>(wv + 8 * Jb + 2 * q);
+            const double2 ab = *reinterpret_cast<const double2*>(av + 8 * Jb + 2 * q);
+            const Pt<D>* pc[4] = {&a0, &a1, &b0, &b1};
+            const double wj[4] = {wa.x, wa.y, wb.x, wb.y}, aj[4] = {aa.x, aa.y, ab.x, ab.y};
+            const double half[4] = {Ja == I ? 0.5 : 1.0, Ja == I ? 0.5 : 1.0,
+                                    Jb == I ? 0.5 : 1.0, Jb == I ? 0.5 : 1.0};
+            double u[4], ph[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) u[e] = sq_dist<D>(pr, *pc[e]);
+            cov_n<F, 4, 1>(u, tab64, ph);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (e < 2 || two) {
+                const double pe = ph[e] * half[e];
+#pragma unroll
+                for (int f = 0; f < D; ++f) {
+                  const double df = pr.x[f] - pc[e]->x[f];
+                  const double g = pe * (df * df);
+                  Ra[f] = fma(g, aj[e], Ra[f]);
+                  Rw[f] = fma(g, wj[e], Rw[f]);
+                }
+              }
+            }
+          };
+#pragma unroll
+          for (int Ja = 0; Ja <= I; Ja += 2) tile_pair(Ja, (Ja + 1 <= I) ? Ja + 1 : Ja, Ja + 1 <= I);
+#pragma unroll
+          for (int f = 0; f < D; ++f) {
+            Gm[f] = fma(xw[I], Ra[f], fma(xa[I], Rw[f], Gm[f]));
+            Gv[f] = fma(2.0 * xw[I], Rw[f], Gv[f]);
+            Gy[f] = fma(2.0 * xa[I], Ra[f], Gy[f]);
+          }
+        }
+      }
+      // cross-covariance row: dc_j / dl_f = phi(s_qj) z_f^2 / l_f
+      double Gmc[D], Gvc[D];
+#pragma unroll
+      for (int f = 0; f < D; ++f) Gmc[f] = Gvc[f] = 0.0;
+      {
+        const Pt<D> pq = ld_pt<D>(pts, k);
+        const int ja = min(lane, k), jb = min(lane + 32, k);
+        const Pt<D> p0 = ld_pt<D>(pts, ja), p1 = ld_pt<D>(pts, jb);
+        const double u[2] = {sq_dist<D>(pq, p0), sq_dist<D>(pq, p1)};
+        double ph[2];
+        cov_n<F, 2, 1>(u, tab64, ph);
+        const double w0 = lane < k ? wv[ja] : 0.0, a0 = lane < k ? av[ja] : 0.0;
+        const double w1 = lane + 32 < k ? wv[jb] : 0.0, a1 = lane + 32 < k ? av[jb] : 0.0;
+#pragma unroll
+        for (int f = 0; f < D; ++f) {
+          const double d0 = pq.x[f] - p0.x[f], d1 = pq.x[f] - p1.x[f];
+          const double g0 = ph[0] * (d0 * d0), g1 = ph[1] * (d1 * d1);
+          Gmc[f] = fma(g0, a0, fma(g1, a1, Gmc[f]));
+          Gvc[f] = fma(g0, w0, fma(g1, w1, Gvc[f]));
+        }
+      }
+      // nugget: dK = I
+      double dwa = 0.0, dww = 0.0, daa = 0.0;
+      for (int e = lane; e < 8 * T; e += 32) {
+        dwa = fma(wv[e], av[e], dwa);
+        dww = fma(wv[e], wv[e], dww);
+        daa = fma(av[e], av[e], daa);
+      }
+      // the quad lanes of a row evaluated different columns of the same row: plain warp sums
+#pragma unroll
+      for (int f = 0; f < D; ++f) {
+        const double rm = warp_sum(Gm[f]), rv = warp_sum(Gv[f]), ry = warp_sum(Gy[f]);
+        const double rmc = warp_sum(Gmc[f]), rvc = warp_sum(Gvc[f]);
+        gdm[f] = (rmc - rm) * loo.inv_len[f];
+        gdv[f] = (rv - 2.0 * rvc) * loo.inv_len[f];
+        gdy[f] = -ry * loo.inv_len[f];
+      }
+      gdm[3] = -warp_sum(dwa);
+      gdv[3] = warp_sum(dww);
+      gdy[3] = -warp_sum(daa);
+    }
+
     // ---- outputs -----------------------------------------------------------------------
     if (lane == 0) {
       if (a.var) a.var[row] = ok ? a.scale * out_var : nan;
@@ -517,20 +718,36 @@ __global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
       if (a.status) a.status[row] = ok ? 0 : 1;
       if (loo.warp_rec) {
         // leave-one-out partials: the target of batch row `row` is train_y[batch index]
+        double* acc = s_acc[warp];
         if (ok) {
           const double err = out_mean - a.train_y[q_src];
           const double e2 = err * err;
-          acc_sq += e2;
-          acc_yky += out_yky;
-          acc_sqv += e2 / out_var;
-          acc_logv += log(out_var);
+          acc[MGP_P_SQERR] += e2;
+          acc[MGP_P_COUNT] += 1.0;
+          acc[MGP_P_YKY] += out_yky;
+          acc[MGP_P_ROWS] += 1.0;
+          acc[MGP_P_SQERR_V] += e2 / out_var;
+          acc[MGP_P_LOGV] += log(out_var);
           if (loo.loss_id == MGP_LOSS_PSEUDO_HUBER) {
             const double z = err / loo.boundary_scale;
-            acc_aux += loo.boundary_scale * loo.boundary_scale * (sqrt(fma(z, z, 1.0)) - 1.0);
+            acc[MGP_P_AUX] += loo.boundary_scale * loo.boundary_scale * (sqrt(fma(z, z, 1.0)) - 1.0);
           }
-          acc_rows += 1;
+          if (GRAD) {
+            const double iv = 1.0 / out_var;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (t < D || t == 3) {
+                double* gr = acc + MGP_PARTIALS + 5 * t;
+                gr[0] += 2.0 * err * gdm[t];            // d sum e^2
+                gr[1] += 2.0 * err * gdm[t] * iv;        // sum 2 e dm / v
+                gr[2] += e2 * gdv[t] * iv * iv;          // sum e^2 dv / v^2
+                gr[3] += gdv[t] * iv;                    // sum dv / v
+                gr[4] += gdy[t];                         // d sum yky
+              }
+            }
+          }
         } else {
-          acc_bad += 1;
+          acc[MGP_P_BAD] += 1.0;
         }
       }
     }
@@ -540,20 +757,18 @@ __global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
   cp_async_wait_all();
 
   if (loo.warp_rec) {
-    // fixed-order reduction: warp records -> (last CTA) 16 strided partial sums per slot ->
-    // sequential sum of the 16.  Bit-reproducible for a given grid; no floating-point atomics.
+    // fixed-order reduction: warps of a block (in order) -> one record per block -> (last
+    // block to finish) strided partial sums per slot -> sequential sum of those.
+    // Bit-reproducible for a given grid; no floating-point atomics.
     __shared__ unsigned int s_last;
-    __shared__ double s_red[16][MGP_PARTIALS];
-    if (lane == 0) {
-      double* rec = loo.warp_rec + (size_t)wglobal * MGP_PARTIALS;
-      rec[MGP_P_SQERR] = acc_sq;
-      rec[MGP_P_COUNT] = (double)acc_rows;
-      rec[MGP_P_YKY] = acc_yky;
-      rec[MGP_P_ROWS] = (double)acc_rows;
-      rec[MGP_P_SQERR_V] = acc_sqv;
-      rec[MGP_P_LOGV] = acc_logv;
-      rec[MGP_P_AUX] = acc_aux;
-      rec[MGP_P_BAD] = (double)acc_bad;
+    constexpr int NGRP = COL_WARPS * 32 / NREC;
+    __shared__ double s_red[NGRP][NREC];
+    __syncthreads();
+    if (threadIdx.x < NREC) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < COL_WARPS; ++w) v += s_acc[w][threadIdx.x];
+      loo.warp_rec[(size_t)blockIdx.x * NREC + threadIdx.x] = v;
     }
     __threadfence();
     __syncthreads();
@@ -561,20 +776,23 @@ __global__ void __launch_bounds__(COL_WARPS * 32, MGP_COL_MINB)
     __syncthreads();
     if (s_last) {
       __threadfence();
-      const int slot = threadIdx.x & 7, grp = threadIdx.x >> 3;  // 128 threads: 16 groups
-      const long long nrec = wstride;
-      double s = 0.0;
-      for (long long w = grp; w < nrec; w += 16)
-        s += __ldcg(loo.warp_rec + (size_t)w * MGP_PARTIALS + slot);
-      s_red[grp][slot] = s;
+      const int slot = threadIdx.x % NREC, grp = threadIdx.x / NREC;
+      double sum = 0.0;
+      for (int c = grp; c < (int)gridDim.x; c += NGRP)
+        sum += __ldcg(loo.warp_rec + (size_t)c * NREC + slot);
+      s_red[grp][slot] = sum;
       __syncthreads();
       __shared__ double s_tot[MGP_PARTIALS];
-      if (threadIdx.x < MGP_PARTIALS) {
+      if (threadIdx.x < NREC) {
         double tot = 0.0;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) tot += s_red[g][threadIdx.x];
-        s_tot[threadIdx.x] = tot;
-        if (loo.peers.world <= 1) loo.partials[threadIdx.x] = tot;
+        for (int g = 0; g < NGRP; ++g) tot += s_red[g][threadIdx.x];
+        if (threadIdx.x < MGP_PARTIALS) {
+          s_tot[threadIdx.x] = tot;
+          if (loo.peers.world <= 1) loo.partials[threadIdx.x] = tot;
+        } else if (GRAD && threadIdx.x < MGP_PARTIALS + MGP_GRAD_DOUBLES) {
+          loo.grad[threadIdx.x - MGP_PARTIALS] = tot;
+        }
       }
       if (threadIdx.x == 0) *loo.counter = 0u;  // ready for the next launch
       if (loo.peers.world > 1) {
@@ -593,16 +811,16 @@ static inline bool col_formula_ok(int formula) {
   return formula == F_M05 || formula == F_M15 || formula == F_M25 || formula == F_GAUSS;
 }
 
-template <int T, int F, int D>
+template <int T, int F, int D, bool GRAD = false>
 int launch_col_one(const TileArgs& a, const ColLoo& loo, long long rows, int* grid_out,
                    cudaStream_t stream) {
   const int pts_doubles = (((a.k + 1) * D) + 1) & ~1;
   const int ys_doubles = (a.k + 2) & ~1;
-  const size_t warp_doubles = col_warp_doubles(T, a.k, D);
+  const size_t warp_doubles = col_warp_doubles(T, a.k, D, GRAD);
   const size_t smem = warp_doubles * COL_WARPS * sizeof(double);
   // the kernel also has static shared memory (reduction scratch)
   cudaFuncAttributes fa;
-  MGP_REQUIRE(cudaFuncGetAttributes(&fa, fused_col_kernel<T, F, D>) == cudaSuccess, MGP_ERR_CUDA,
+  MGP_REQUIRE(cudaFuncGetAttributes(&fa, fused_col_kernel<T, F, D, GRAD>) == cudaSuccess, MGP_ERR_CUDA,
               "cudaFuncGetAttributes failed");
   const size_t smem_cap = (size_t)max_smem_optin() - fa.sharedSizeBytes;
   MGP_REQUIRE(smem <= smem_cap, MGP_ERR_UNSUPPORTED,
@@ -611,12 +829,12 @@ int launch_col_one(const TileArgs& a, const ColLoo& loo, long long rows, int* gr
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(fused_col_kernel<T, F, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(fused_col_kernel<T, F, D, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem_cap);
     attr_set[dev] = true;
   }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_col_kernel<T, F, D>,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_col_kernel<T, F, D, GRAD>,
                                                     COL_WARPS * 32, smem) != cudaSuccess ||
       per_sm < 1)
     per_sm = 1;
@@ -628,7 +846,7 @@ int launch_col_one(const TileArgs& a, const ColLoo& loo, long long rows, int* gr
     blocks = *grid_out > 0 ? *grid_out : cap;
     *grid_out = (int)blocks;
   }
-  fused_col_kernel<T, F, D><<<(unsigned)blocks, COL_WARPS * 32, smem, stream>>>(
+  fused_col_kernel<T, F, D, GRAD><<<(unsigned)blocks, COL_WARPS * 32, smem, stream>>>(
       a, loo, pts_doubles, ys_doubles, (int)warp_doubles);
   return check_launch("fused_col_kernel");
 }

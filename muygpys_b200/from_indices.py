@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from copy import deepcopy
 
+import numpy as np
+
 from . import fused, ops
 from ._arrays import fdev, idev, like_input
 from .adapt import ModelSpec
@@ -77,10 +79,32 @@ def _lbfgsb(muygps, obj_fn, verbose=False, **kwargs):
     return new
 
 
+def _lbfgsb_with_gradient(muygps, value_and_grad, verbose=False, **kwargs):
+    """scipy L-BFGS-B with jac=True: one kernel launch per iteration instead of 1 + p."""
+    from scipy import optimize as sciopt
+
+    names, x0, bounds = muygps.get_opt_params()
+    names = [str(n) for n in names]
+
+    def fun(xv):
+        val, grads = value_and_grad(**dict(zip(names, xv)))
+        return -val, -np.array([grads[n] for n in names])
+
+    res = sciopt.minimize(fun, x0, method="L-BFGS-B", jac=True, bounds=bounds, **kwargs)
+    if verbose:
+        print(res)
+    new = deepcopy(muygps)
+    for name, val, (lo, hi) in zip(names, res.x, bounds):
+        target = new.noise if name == "noise" else new.kernel._hyperparameters[name]
+        target._set_val(min(max(float(val), lo), hi))
+    new._make()
+    return new
+
+
 def optimize_from_indices(muygps, batch_indices, batch_nn_indices, train_features,
                           train_targets, loss_fn=None, opt_fn=None, verbose: bool = False,
                           loss_kwargs=None, target_mask=None, group=None,
-                          distributed: bool = False, **kwargs):
+                          distributed: bool = False, use_gradient: bool = False, **kwargs):
     """`optimize_from_indices` (S/examples/from_indices.py:126-223) with the fused objective.
 
     The outer loop is the reference's own: `opt_fn` is a `MuyGPyS.optimize.OptimizeFn`
@@ -89,6 +113,14 @@ def optimize_from_indices(muygps, batch_indices, batch_nn_indices, train_feature
     the one-launch `obj_fn`; only the objective changes."""
     if loss_fn is None:
         from .losses import lool_fn as loss_fn
+    if use_gradient:
+        # analytic gradient from the same launch (SURVEY.md 8f-2): L-BFGS-B with jac=True
+        from .objective import make_fused_loo_value_and_grad_fn
+
+        vg = make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
+                                              train_features, train_targets, group=group,
+                                              distributed=distributed)
+        return _lbfgsb_with_gradient(muygps, vg, verbose=verbose, **kwargs)
     obj_fn = make_fused_loo_crossval_fn(
         muygps, loss_fn, batch_indices, batch_nn_indices, train_features, train_targets,
         target_mask=target_mask, loss_kwargs=loss_kwargs, group=group, distributed=distributed)

@@ -14,6 +14,7 @@ from __future__ import annotations
 import math
 from typing import Callable, Dict, Optional
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -189,3 +190,77 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
         return -float(to_host(rec2)[L.P_AUX])
 
     return obj_fn
+
+
+def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
+                                     train_features, train_targets, group=None,
+                                     distributed: bool = False) -> Callable:
+    """`fn(**theta) -> (objective, {name: d objective / d name})` with the ANALYTIC gradient
+    (SURVEY.md 8f-2): one launch of `mgp_fused_loo_grad` per call, where the reference's
+    optimiser needs 1 + p objective evaluations for its finite differences
+    (S/_src/optimize/chassis/numpy.py:68-74).  The objective is the negated loss, as
+    `make_loo_crossval_fn` returns it.  Supported: mse and lool (fixed scale, or analytic scale
+    with iteration_count == 1 and a fixed nugget), one response, the shapes of `mgp_fused_loo`.
+    Gradient names follow the optimiser's keywords: `length_scale` | `length_scale0..`,
+    `noise`."""
+    spec = ModelSpec.of(muygps)
+    loss_fn = as_loss(loss_fn)
+    x = fdev(train_features)
+    y = fdev(train_targets)
+    bi, bnn = idev(batch_indices), idev(batch_nn_indices)
+    k = bnn.shape[1]
+    d = 1 if x.dim() == 1 else x.shape[1]
+    r = 1 if y.dim() == 1 else y.shape[1]
+    if loss_fn.loss_id not in (L.LOSS_MSE, L.LOSS_LOOL):
+        raise NotImplementedError(f"analytic gradient: loss {loss_fn.name} (mse and lool only)")
+    if not ops.fused_loo_supported(d, k, r, spec.kernel_id, spec.metric_id, spec.heteroscedastic):
+        raise NotImplementedError("analytic gradient: shape not supported by mgp_fused_loo_grad")
+    lool = loss_fn.loss_id == L.LOSS_LOOL
+    analytic = lool and spec.analytic
+    if analytic and spec.iteration_count != 1:
+        raise NotImplementedError("analytic gradient with AnalyticScale(iteration_count > 1)")
+    loo = ops.FusedLoo(x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
+                       loss_id=loss_fn.loss_id, want_grad=True)
+    model_noise = spec.noise(None)
+
+    def fn(*args, **theta):
+        if analytic and "noise" in theta and float(theta["noise"]) != float(model_noise):
+            raise NotImplementedError(
+                "analytic gradient: the analytic scale ignores the optimiser's nugget "
+                "(S/gp/hyperparameter/scale.py:206-208); optimise the nugget by finite differences")
+        rec = loo.record(loo.launch(spec.length_scale_arg(**theta),
+                                    spec.noise(theta.get("noise"))))
+        g = loo.grad.numpy().reshape(L.MGP_GRAD_PARAMS, 5).copy()
+        if distributed:
+            from .distributed import allreduce_partials
+
+            both = torch.as_tensor(np.concatenate((rec, g.ravel()))).to(x.device)
+            allreduce_partials(both, group)  # per-rank sums of the record and the gradient
+            both = both.cpu().numpy()
+            rec, g = both[:8], both[8:].reshape(L.MGP_GRAD_PARAMS, 5)
+        rows = rec[L.P_ROWS]
+        if lool:
+            S = rec[L.P_SQERR_V]
+            sigma2 = rec[L.P_YKY] / (rows * k) if analytic else spec.scale()
+            value = S / sigma2 + rec[L.P_LOGV] + rows * math.log(sigma2)
+
+            def dloss(t):
+                dsig = t[4] / (rows * k) if analytic else 0.0
+                return ((t[1] - t[2]) / sigma2 + t[3]
+                        + dsig * (-S / (sigma2 * sigma2) + rows / sigma2))
+        else:
+            value = rec[L.P_SQERR] / rec[L.P_COUNT]
+
+            def dloss(t):
+                return t[0] / rec[L.P_COUNT]
+
+        grads = {}
+        if spec.anisotropic:
+            for f in range(d):
+                grads[f"length_scale{f}"] = -float(dloss(g[f]))
+        else:
+            grads["length_scale"] = -float(dloss(g[:d].sum(axis=0)))
+        grads["noise"] = -float(dloss(g[3]))
+        return -float(value), grads
+
+    return fn

@@ -248,7 +248,8 @@ class FusedLoo:
 
     @_on_tensor_device
     def __init__(self, train_x, train_y, batch_idx, nn_idx, *, kernel_id, metric_id, loss_id,
-                 boundary_scale=1.0, partials: Optional[torch.Tensor] = None):
+                 boundary_scale=1.0, partials: Optional[torch.Tensor] = None,
+                 want_grad: bool = False):
         lib = L.lib()
         self.x = as_2d(fdev(train_x, "train_features"))
         y = fdev(train_y, "train_targets")
@@ -278,7 +279,11 @@ class FusedLoo:
         self.loss_id = int(loss_id)
         self.boundary_scale = float(boundary_scale)
         self._lib = lib
-        self._fn = lib.mgp_fused_loo_peers
+        self._fn = lib.mgp_fused_loo_grad
+        # gradient sums (MGP_GRAD_DOUBLES), written by the same kernel into pinned host memory
+        self.grad = torch.zeros((L.MGP_GRAD_DOUBLES,), dtype=f64).pin_memory() if want_grad \
+            else None
+        self._grad_ptr = _p(self.grad)
         self._pref = C.byref(self.p)
         self._out = _p(self.partials)
         self._ws = _p(self.ws)
@@ -302,8 +307,8 @@ class FusedLoo:
             self.p.length_scale_count = len(ls)
         self.p.noise = float(noise)
         g = None if peers is None else C.byref(peers.group_struct())
-        rc = self._fn(self._pref, self.loss_id, self.boundary_scale, self._out, self._ws,
-                      self.ws_bytes, g, _stream())
+        rc = self._fn(self._pref, self.loss_id, self.boundary_scale, self._out, self._grad_ptr,
+                      self._ws, self.ws_bytes, g, _stream())
         if rc != 0:
             L.check(rc)
         return self.partials

@@ -1,0 +1,117 @@
+"""GPU: analytic gradient of the LOO objective from the fused kernel against
+central finite differences of (a) the numpy oracle's objective and (b) the fused objective
+itself, 1e-6 relative; and L-BFGS-B with jac=True reaching the finite-difference optimum."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(seed, n, b, d, k):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(size=(n, d))
+    y = np.sin(4 * x[:, 0]) + (np.cos(3 * x[:, -1]) if d > 1 else 0.0) + 0.05 * rng.normal(size=n)
+    bi = np.sort(rng.choice(n, b, replace=False))
+    bnn, _ = O.knn_batch(x, bi, k)
+    return x, y, bi, np.ascontiguousarray(bnn)
+
+
+def _model(kernel, ls, noise, analytic, noise_bounds=None):
+    from muygpys_b200.gp import MuyGPS
+    from muygpys_b200.gp.deformation import F2, Anisotropy, Isotropy, l2
+    from muygpys_b200.gp.hyperparameter import (AnalyticScale, FixedScale, Parameter,
+                                                VectorParameter)
+    from muygpys_b200.gp.kernels import RBF, Matern
+    from muygpys_b200.gp.noise import HomoscedasticNoise
+
+    metric = F2 if kernel == "rbf" else l2
+    if isinstance(ls, (list, tuple)):
+        deformation = Anisotropy(metric, VectorParameter(*[Parameter(v, (v * 0.2, v * 5)) for v in ls]))
+    else:
+        deformation = Isotropy(metric, Parameter(ls, (ls * 0.2, ls * 5)))
+    kern = RBF(deformation=deformation) if kernel == "rbf" else Matern(
+        smoothness=Parameter(kernel), deformation=deformation)
+    scale = AnalyticScale() if analytic else FixedScale()
+    if not analytic:
+        scale._set(1.3)
+    nz = HomoscedasticNoise(noise, noise_bounds) if noise_bounds else HomoscedasticNoise(noise)
+    return MuyGPS(kernel=kern, noise=nz, scale=scale)
+
+
+CASES = [
+    # kernel, length scale(s), d, k, loss, analytic scale, nugget gradient checked
+    (1.5, 0.3, 2, 50, "lool", True, False),
+    (1.5, 0.3, 2, 50, "mse", False, True),
+    (2.5, [0.3, 0.6], 2, 30, "lool", False, True),
+    (0.5, [0.4, 0.3, 0.5], 3, 23, "lool", True, False),
+    ("rbf", 0.2, 1, 30, "mse", False, True),
+    (np.inf, 0.4, 2, 47, "lool", True, False),   # k % 8 == 7: augmented rows straddle tiles
+    (1.5, 0.25, 2, 62, "lool", False, True),
+]
+
+
+@pytest.mark.parametrize("kernel,ls,d,k,loss,analytic,check_noise", CASES)
+def test_analytic_gradient_matches_finite_differences(kernel, ls, d, k, loss, analytic,
+                                                      check_noise):
+    from muygpys_b200.optimize import loss as losses
+    from muygpys_b200.optimize.objective import (make_fused_loo_crossval_fn,
+                                                 make_fused_loo_value_and_grad_fn)
+
+    x, y, bi, bnn = _setup(hash((d, k)) % 1000, 3000, 400, d, k)
+    noise = 2e-3
+    model = _model(kernel, ls, noise, analytic)
+    lf = getattr(losses, f"{loss}_fn")
+    vg = make_fused_loo_value_and_grad_fn(model, lf, bi, bnn, x, y)
+    obj = make_fused_loo_crossval_fn(model, lf, bi, bnn, x, y)
+    aniso = isinstance(ls, list)
+    theta = ({f"length_scale{i}": v * 1.1 for i, v in enumerate(ls)} if aniso
+             else {"length_scale": ls * 1.1})
+    val, grads = vg(**theta)
+    assert abs(val - obj(**theta)) <= 1e-12 * abs(val)
+    names = list(theta) + (["noise"] if check_noise else [])
+    for name in names:
+        base = theta.get(name, noise)
+        h = 1e-5 * base
+        up = dict(theta, **{name: base + h})
+        dn = dict(theta, **{name: base - h})
+        fd = (obj(**up) - obj(**dn)) / (2 * h)
+        assert abs(grads[name] - fd) <= 2e-6 * max(abs(fd), 1e-3 * abs(val) / base), (
+            name, grads[name], fd)
+
+
+def test_gradient_against_oracle_objective():
+    """Finite differences of the ORACLE's objective (numpy restatement of the reference's
+    make_loo_crossval_fn), so the check does not lean on our own kernels."""
+    from muygpys_b200.optimize.loss import lool_fn
+    from muygpys_b200.optimize.objective import make_fused_loo_value_and_grad_fn
+
+    x, y, bi, bnn = _setup(5, 2000, 150, 2, 50)
+    model = _model(1.5, 0.3, 1e-3, True)
+    vg = make_fused_loo_value_and_grad_fn(model, lool_fn, bi, bnn, x, y)
+    ls = 0.27
+    val, grads = vg(length_scale=ls)
+
+    def oracle(l):
+        return O.loo_objective(O.LOSS_LOOL, O.KERNEL_MATERN_15, O.METRIC_L2, l, 1e-3, x, y, bi,
+                               bnn)[0]
+
+    assert abs(val - oracle(ls)) <= 1e-10 * abs(val)
+    h = 1e-5 * ls
+    fd = (oracle(ls + h) - oracle(ls - h)) / (2 * h)
+    assert abs(grads["length_scale"] - fd) <= 1e-6 * abs(fd), (grads, fd)
+
+
+def test_lbfgsb_with_gradient_reaches_the_finite_difference_optimum():
+    from muygpys_b200.examples.from_indices import optimize_from_indices
+    from muygpys_b200.optimize.loss import lool_fn
+
+    x, y, bi, bnn = _setup(9, 6000, 1500, 2, 30)
+    model = _model(2.5, [0.3, 0.6], 1e-3, True)
+    fd_opt = optimize_from_indices(model, bi, bnn, x, y, loss_fn=lool_fn)
+    gr_opt = optimize_from_indices(model, bi, bnn, x, y, loss_fn=lool_fn, use_gradient=True)
+    a, b = fd_opt.get_opt_params()[1], gr_opt.get_opt_params()[1]
+    np.testing.assert_allclose(b, a, rtol=2e-3)
