@@ -313,6 +313,8 @@ int mgp_rowdot(const double* Kcross, const double* coeffs, int64_t b, int32_t k,
  *   mode 2: even warps mode 0, odd warps mode 1 (pipe-sharing test)
  *   mode 3: one dependent DFMA chain per thread (latency)
  *   mode 4: one dependent DMMA chain per warp (latency)
+ *   mode 5: 8 independent SHFL.IDX per thread per iteration (shuffle issue rate)
+ *   mode 6: one dependent SHFL.IDX chain per thread (shuffle latency)
  * `sink` is a device buffer of blocks*threads doubles.  Timed by the caller. */
 int mgp_fp64_probe(int32_t mode, int32_t blocks, int32_t threads, int32_t iters, double* sink,
                    void* stream);

@@ -32,6 +32,21 @@ __global__ void probe_kernel(int mode, int iters, double* __restrict__ sink) {
       dmma(c[4], c[5], x, y); dmma(c[6], c[7], x, y);
     }
     sink[gid] = c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7];
+  } else if (m == 5) {  // shuffle issue rate: 8 independent SHFL.IDX per iteration
+    int v0 = gid, v1 = gid + 1, v2 = gid + 2, v3 = gid + 3, v4 = gid + 4, v5 = gid + 5,
+        v6 = gid + 6, v7 = gid + 7;
+    const int src = (threadIdx.x * 5 + 3) & 31;
+    for (int i = 0; i < iters; ++i) {
+      v0 = __shfl_sync(0xffffffffu, v0, src); v1 = __shfl_sync(0xffffffffu, v1, src);
+      v2 = __shfl_sync(0xffffffffu, v2, src); v3 = __shfl_sync(0xffffffffu, v3, src);
+      v4 = __shfl_sync(0xffffffffu, v4, src); v5 = __shfl_sync(0xffffffffu, v5, src);
+      v6 = __shfl_sync(0xffffffffu, v6, src); v7 = __shfl_sync(0xffffffffu, v7, src);
+    }
+    sink[gid] = (double)(v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7);
+  } else if (m == 6) {  // shuffle latency: one dependent chain
+    int v0 = gid;
+    for (int i = 0; i < iters; ++i) v0 = __shfl_sync(0xffffffffu, v0, (v0 + 1) & 31);
+    sink[gid] = (double)v0;
   } else if (m == 3) {
     double a0 = 0;
     for (int i = 0; i < iters; ++i) a0 = fma(a0, x, y);
@@ -48,7 +63,7 @@ __global__ void probe_kernel(int mode, int iters, double* __restrict__ sink) {
 extern "C" int mgp_fp64_probe(int32_t mode, int32_t blocks, int32_t threads, int32_t iters,
                               double* sink, void* stream) {
   using namespace mgp;
-  MGP_REQUIRE(mode >= 0 && mode <= 4, MGP_ERR_BAD_ARG, "unknown probe mode %d", mode);
+  MGP_REQUIRE(mode >= 0 && mode <= 6, MGP_ERR_BAD_ARG, "unknown probe mode %d", mode);
   MGP_REQUIRE(blocks >= 1 && threads >= 32 && threads <= 1024 && (threads % 32) == 0 &&
                   iters >= 1 && sink,
               MGP_ERR_BAD_ARG, "bad probe launch parameters");
