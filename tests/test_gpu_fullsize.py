@@ -160,7 +160,8 @@ def test_c2_objective_shards_combine(c2):
 
 
 def test_c4_shape_anisotropic_k100_lool():
-    """C4 shape: anisotropic Matern 5/2, k=100, lool (generic kernel: k=100 exceeds one warp)."""
+    """C4 at full size: anisotropic Matern 5/2, 10 M training points, k=100, lool, 10 k batch
+    rows (one GPU's share of the 80 k-row batch); oracle check on a subsample."""
     from muygpys_b200.gp import MuyGPS
     from muygpys_b200.gp.deformation import Anisotropy, l2
     from muygpys_b200.gp.hyperparameter import AnalyticScale, Parameter, VectorParameter
@@ -171,7 +172,7 @@ def test_c4_shape_anisotropic_k100_lool():
     from muygpys_b200.optimize.objective import make_fused_loo_crossval_fn
 
     rng = np.random.default_rng(4)
-    n, b, k = 2_000_000, 4_000, 100
+    n, b, k = 10_000_000, 10_000, 100
     x = rng.uniform(size=(n, 2))
     y = np.sin(2 * np.pi * x[:, 0]) * np.cos(2 * np.pi * x[:, 1] / 5) + 0.05 * rng.normal(size=n)
     xd, yd = dev(x), dev(y)
@@ -183,7 +184,7 @@ def test_c4_shape_anisotropic_k100_lool():
     obj = make_fused_loo_crossval_fn(model, lool_fn, dev(bi), bnn, xd, yd)
     got = obj(length_scale0=0.12, length_scale1=0.4)
     assert np.isfinite(got) and got == obj(length_scale0=0.12, length_scale1=0.4)
-    sub = np.arange(0, b, 10)
+    sub = np.arange(0, b, 25)
     sub_obj = make_fused_loo_crossval_fn(model, lool_fn, dev(bi[sub]), bnn[dev(sub)], xd, yd)
     want, _ = O.loo_objective(O.LOSS_LOOL, O.KERNEL_MATERN_25, O.METRIC_L2,
                               np.array([0.12, 0.4]), 1e-3, x, y, bi[sub],
@@ -263,3 +264,72 @@ def test_c5_shape_10m_train_mean_var_and_fast_mean():
         O.homoscedastic_perturb(Kin, 1e-3), y[nf][..., None])[..., 0])
     assert_close(fast.cpu().numpy()[srows, 0], want, 1e-9, "C5 fast mean")
     assert fast_nn_update(cnn[:, 1:]).shape == cnn[:, 1:].shape
+
+
+def test_c5_full_size_100m_train_10m_test():
+    """C5 at FULL size: 100 M training points (the grid index's largest exercised size), 10 M
+    test points, Matern 1/2, k = 50: exact KNN, posterior mean + variance, and the fast
+    posterior mean; spot checks against the numpy oracle with brute-force neighbours on the
+    host.  Data are generated on the device (2.4 GB of host random numbers per run would
+    dominate the test) and only the rows the oracle needs are copied back."""
+    from muygpys_b200 import ops
+    from muygpys_b200.neighbors import NN_Wrapper
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~60 GB of free device memory")
+    n, t, k = 100_000_000, 10_000_000, 50
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    xd = torch.rand((n, 2), generator=gen, device="cuda", dtype=torch.float64)
+    yd = (torch.sin(4 * xd[:, 0]) + torch.cos(3 * xd[:, 1]) + 0.3 * torch.sin(11 * xd[:, 0] * xd[:, 1])
+          + 0.05 * torch.randn(n, generator=gen, device="cuda", dtype=torch.float64))
+    qd = torch.rand((t, 2), generator=gen, device="cuda", dtype=torch.float64)
+    nbrs = NN_Wrapper(xd, k)
+    assert nbrs._grid is not None and nbrs._grid.n == n
+    nn, d2 = nbrs._query(qd, k)
+    assert nn.shape == (t, k) and int(nn.min()) >= 0 and int(nn.max()) < n
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all()), "neighbours sorted by distance"
+    # brute-force neighbours of a few queries on the host (100 M distances each)
+    x = xd.cpu().numpy()
+    rows = np.array([0, 1, 4_999_999, 9_999_999, 123_456, 7_654_321])
+    q_rows = qd[torch.as_tensor(rows).cuda()].cpu().numpy()
+    for i, r in enumerate(rows):
+        diff = x - q_rows[i]
+        dist = diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]
+        order = np.argpartition(dist, k)[:k]
+        order = order[np.lexsort((order, dist[order]))]
+        np.testing.assert_array_equal(nn[r].cpu().numpy(), order)
+    kw = dict(kernel_id=O.KERNEL_MATERN_05, metric_id=O.METRIC_L2, length_scale=0.1, noise=1e-3)
+    out = ops.fused_posterior(xd, qd, None, nn, yd, want_status=True, **kw)
+    assert int(out["status"].sum()) == 0 and bool(torch.isfinite(out["mean"]).all())
+    assert bool((out["var"] > 0).all()) and bool((out["var"] < 1.0).all())
+    # oracle on the checked rows: gather their neighbourhoods into a small problem
+    sel = nn[torch.as_tensor(rows).cuda()].cpu().numpy()
+    uniq, inv = np.unique(sel, return_inverse=True)
+    ud = torch.as_tensor(uniq).cuda()
+    mean, var = O.predict(O.KERNEL_MATERN_05, O.METRIC_L2, 0.1, 1e-3, 1.0, xd[ud].cpu().numpy(),
+                          yd[ud].cpu().numpy(), q_rows, np.arange(len(rows)),
+                          inv.reshape(sel.shape))
+    assert_close(out["mean"].cpu().numpy()[rows, 0], mean, RTOL, "C5 full-size mean")
+    assert_close(out["var"].cpu().numpy()[rows], var, RTOL, "C5 full-size variance")
+    # fast posterior mean: coefficients of the training points that are some test point's
+    # nearest neighbour, then a k-dot per test point; equals the definition on the checked rows
+    closest = torch.unique(nn[:, 0])
+    cnn, _ = nbrs._query(xd[closest], k)
+    assert torch.equal(cnn[:, 0], closest)
+    coeffs = ops.fused_posterior(xd, xd, closest, cnn, yd, want_mean=False, want_var=False,
+                                 want_coeffs=True, **kw)["coeffs"]
+    slot = torch.searchsorted(closest, nn[:, 0].contiguous())
+    nn_fast = cnn[slot]
+    fast = ops.fast_mean(xd, qd, None, nn_fast, slot, coeffs, kernel_id=O.KERNEL_MATERN_05,
+                         metric_id=O.METRIC_L2, length_scale=0.1)
+    nf = nn_fast[torch.as_tensor(rows).cuda()].cpu().numpy()
+    uniq, inv = np.unique(nf, return_inverse=True)
+    ud = torch.as_tensor(uniq).cuda()
+    xs, ys = xd[ud].cpu().numpy(), yd[ud].cpu().numpy()
+    nfl = inv.reshape(nf.shape)
+    Kin, Kcross = O.kernel_tensors(O.KERNEL_MATERN_05, O.METRIC_L2, 0.1, xs, q_rows,
+                                   np.arange(len(rows)), nfl)
+    want = np.einsum("bk,bk->b", Kcross, np.linalg.solve(
+        O.homoscedastic_perturb(Kin, 1e-3), ys[nfl][..., None])[..., 0])
+    assert_close(fast.cpu().numpy()[rows, 0], want, 1e-9, "C5 full-size fast mean")
