@@ -41,8 +41,11 @@ __device__ __noinline__ void assemble(double* __restrict__ tiles, const double* 
                      : sqdist<(D < 0 ? 0 : D)>(pts, (p[w] >> 8) & 255, p[w] & 255, d);
 #pragma unroll
     for (int w = 0; w < W; ++w) v[w] = neg_cov<F>(u[w], tab64, post_scale, kernel_id);
+    // lanes past the end evaluated the dummy entry: do not store it (every such lane would
+    // write the same scratch cell -- harmless, but a write-write hazard for racecheck)
 #pragma unroll
-    for (int w = 0; w < W; ++w) tiles[p[w] >> 16] = v[w];
+    for (int w = 0; w < W; ++w)
+      if (base + 32 * w + lane < n_elem) tiles[p[w] >> 16] = v[w];
   }
 }
 
