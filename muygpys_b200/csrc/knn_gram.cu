@@ -19,11 +19,13 @@
 //
 // So the returned indices and squared distances are always bit-identical to the brute-force
 // kernels'; only the amount of work depends on the data.
+#include <cuda.h>
 #include <float.h>
 #include <limits.h>
 
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "smem_heap.cuh"
@@ -81,21 +83,85 @@ __device__ __forceinline__ void kg_cp_async8(void* smem_dst, const void* gmem_sr
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
 
-// VEC: d even and both arrays 16-byte aligned -> 16-byte asynchronous copies
-template <bool VEC, typename IdxT>
+// ---- TMA (cp.async.bulk.tensor) + mbarrier plumbing for the operand tiles ------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// wait for the phase with the given parity; a copy that never lands traps instead of hanging
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();
+}
+// box of a 2-D tensor map (coordinates: c0 = feature, c1 = row) -> shared memory
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1,
+                                            unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+constexpr int KG_TF = 16;  // features per TMA box: 128 bytes, the span of the 128-byte swizzle
+// element (row r, feature f < 16) of a 64 x 16 box written with CU_TENSOR_MAP_SWIZZLE_128B:
+// the 16-byte chunk index is XORed with the row (mod 8), so the 8 rows a fragment load touches
+// land in 8 different bank groups (a dense 128-byte pitch would be an 8-way conflict)
+__device__ __forceinline__ double box_ld(const double* box, int r, int f) {
+  return box[r * KG_TF + ((((f >> 1) ^ (r & 7)) << 1) | (f & 1))];
+}
+
+// VEC: d even and both arrays 16-byte aligned -> 16-byte asynchronous copies.
+// NST > 0: the operand tiles arrive by TMA (cp.async.bulk.tensor, one thread issues two box
+// copies per stage into an NST-deep ring guarded by mbarriers; out-of-range rows / features are
+// zero-filled by the copy engine); NST == 0: thread-issued cp.async into two buffers.
+template <bool VEC, typename IdxT, int NST>
 __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
     const double* __restrict__ train, long long n, const double* __restrict__ queries,
     long long q, int d, int kk, const int64_t* __restrict__ self_idx,
     const double* __restrict__ xn, const double* __restrict__ qn, long long split_len,
     int nsplit, int32_t* __restrict__ part_idx, double* __restrict__ part_s,
-    int64_t* __restrict__ cand_idx, double* __restrict__ cand_s) {
+    int64_t* __restrict__ cand_idx, double* __restrict__ cand_s,
+    const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmx) {
+  constexpr bool TMA = NST > 0;
   // two staging buffers filled with cp.async (the copy of chunk t + 1 runs under the DMMAs of
   // chunk t); the 64 x 65 tile of S~ reuses the buffer that was consumed last
-  extern __shared__ double stage[];
+  // the swizzle pattern of the TMA boxes is a function of the shared-memory ADDRESS: the ring
+  // must start on a 1024-byte boundary (8 rows x 128 bytes)
+  extern __shared__ __align__(1024) unsigned char kg_raw[];
+  double* stage =
+      reinterpret_cast<double*>(kg_raw + ((1024u - (smem_u32(kg_raw) & 1023u)) & 1023u));
   __shared__ double worst_sh[KG_Q];
   __shared__ __align__(8) unsigned short mask_sh[4 * KG_Q];
-  constexpr int BUF = 2 * KG_Q * KG_LD;
-  static_assert(KG_Q * (KG_X + 1) <= BUF, "S~ tile must fit one staging buffer");
+  __shared__ __align__(8) unsigned long long full_bar[TMA ? NST : 1];   // stage has landed
+  __shared__ __align__(8) unsigned long long empty_bar[TMA ? NST : 1];  // all 8 warps are done
+  constexpr int FW = TMA ? KG_TF : KG_F;  // features per stage
+  constexpr int BUF = TMA ? 2 * KG_Q * KG_TF : 2 * KG_Q * KG_LD;
+  constexpr int NBUF = TMA ? NST : 2;
+  constexpr int DS = KG_Q * (KG_X + 1);   // the S~ tile (TMA: its own area behind the ring)
+  static_assert(TMA || DS <= BUF, "S~ tile must fit one staging buffer");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rho = lane >> 2, q4 = lane & 3;
   const int tr0 = 2 * (warp & 3);   // this warp's two tile rows (queries)
@@ -110,7 +176,7 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
   // Rows are stored as offsets into this CTA's slice of the training set: 16 bits when the
   // slice is short enough, which is what lets two CTAs share an SM up to k = 50.
   SmemHeapT<IdxT> top;
-  top.hd = stage + 2 * BUF;
+  top.hd = stage + NBUF * BUF + (TMA ? DS + 1 : 0);
   top.hi = reinterpret_cast<IdxT*>(top.hd + (size_t)kk * KG_Q);
   top.nt = KG_Q;
   top.t = tid;
@@ -129,7 +195,7 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
 
   const long long x_begin = (long long)blockIdx.y * split_len;
   const long long x_end = min(n, x_begin + split_len);
-  const int nchunks = (d + KG_F - 1) / KG_F;
+  const int nchunks = (d + FW - 1) / FW;
   const long long ntiles = x_end > x_begin ? (x_end - x_begin + KG_X - 1) / KG_X : 0;
   const long long total = ntiles * nchunks;
 
@@ -161,11 +227,44 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
+  // TMA: one thread arms the stage's barrier with the byte count and issues the two box copies
+  auto issue_tma = [&](long long x0, int f0, int buf) {
+    if (tid == 0) {
+      const unsigned bar = smem_u32(&full_bar[buf]);
+      mbar_expect_tx(bar, 2 * KG_Q * KG_TF * (unsigned)sizeof(double));
+      tma_load_2d(smem_u32(stage + buf * BUF), &tmq, f0, (int)q0, bar);
+      tma_load_2d(smem_u32(stage + buf * BUF + KG_Q * KG_TF), &tmx, f0, (int)x0, bar);
+    }
+  };
+  if (TMA) {
+    if (tid == 0) {
+      for (int i = 0; i < NBUF; ++i) {
+        mbar_init(smem_u32(&full_bar[i]), 1);
+        mbar_init(smem_u32(&empty_bar[i]), 8);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+  }
+
   double acc[2][4][2];
-  if (total > 0) issue(x_begin, 0, 0);
+  // issue cursor (TMA: NST stages ahead of the compute cursor)
+  long long ix0 = x_begin;
+  int ichunk = 0;
+  auto issue_next = [&](int buf) {
+    if (TMA) issue_tma(ix0, ichunk * FW, buf);
+    else issue(ix0, ichunk * FW, buf);
+    if (++ichunk == nchunks) {
+      ichunk = 0;
+      ix0 += KG_X;
+    }
+  };
+  long long issued = 0;
+  for (; issued < total && issued < (TMA ? NBUF : 1); ++issued) issue_next((int)issued);
   long long x0 = x_begin;  // current stage
   int chunk = 0, buf = 0;
-  for (long long st = 0; st < total; ++st, buf ^= 1) {
+  for (long long st = 0; st < total; ++st, buf = (buf + 1 == NBUF) ? 0 : buf + 1) {
     // the stage after this one
     int nchunk = chunk + 1;
     long long nx0 = x0;
@@ -173,9 +272,16 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
       nchunk = 0;
       nx0 += KG_X;
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();  // this stage has landed; nobody still reads the other buffer
-    if (st + 1 < total) issue(nx0, nchunk * KG_F, buf ^ 1);
+    if (TMA) {
+      mbar_wait(smem_u32(&full_bar[buf]), (unsigned)((st / NBUF) & 1));
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();  // this stage has landed; nobody still reads the other buffer
+      if (issued < total) {
+        issue_next(buf ^ 1);
+        ++issued;
+      }
+    }
     if (chunk == 0) {
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -183,26 +289,49 @@ __global__ void __launch_bounds__(256, 2) knn_gram_filter_kernel(
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
     const double* Qs = stage + buf * BUF;
-    const double* Xs = Qs + KG_Q * KG_LD;
-    const int ksteps = (min(KG_F, d - chunk * KG_F) + 3) >> 2;
+    const double* Xs = Qs + (TMA ? KG_Q * KG_TF : KG_Q * KG_LD);
+    const int ksteps = (min(FW, d - chunk * FW) + 3) >> 2;
     for (int ks = 0; ks < ksteps; ++ks) {
       double a[2], b[4];
+      if (TMA) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) a[i] = Qs[(8 * (tr0 + i) + rho) * KG_LD + 4 * ks + q4];
+        for (int i = 0; i < 2; ++i) a[i] = box_ld(Qs, 8 * (tr0 + i) + rho, 4 * ks + q4);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Xs[(8 * (tc0 + j) + rho) * KG_LD + 4 * ks + q4];
+        for (int j = 0; j < 4; ++j) b[j] = box_ld(Xs, 8 * (tc0 + j) + rho, 4 * ks + q4);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = Qs[(8 * (tr0 + i) + rho) * KG_LD + 4 * ks + q4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Xs[(8 * (tc0 + j) + rho) * KG_LD + 4 * ks + q4];
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (TMA) {
+      // No block-wide barrier per stage: each warp releases the stage on its `empty` barrier
+      // and moves on; the issuing thread refills the PREVIOUS stage's buffer (which the other
+      // warps have almost certainly left) once all eight warps have released it, so the copy
+      // engine runs NST - 1 stages ahead of the slowest warp.
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&empty_bar[buf]));
+      if (st >= 1 && issued < total) {
+        const int pbuf = (buf == 0) ? NBUF - 1 : buf - 1;
+        if (tid == 0) mbar_wait(smem_u32(&empty_bar[pbuf]), (unsigned)(((st - 1) / NBUF) & 1));
+        issue_next(pbuf);
+        ++issued;
+      }
     }
     if (chunk != nchunks - 1) {
       chunk = nchunk;
       continue;
     }
     // ---- a train tile is complete: S~ to the owners of the candidate lists ----------------
-    double* Ds = stage + buf * BUF;
-    __syncthreads();  // everyone is done with the staged features of this buffer
+    double* Ds = TMA ? stage + NBUF * BUF : stage + buf * BUF;
+    // non-TMA: everyone is done with the staged features of this buffer; TMA: the owners are
+    // done with the previous S~ tile (warps run up to NST stages apart)
+    __syncthreads();
     // accumulator layout: lane (rho, q4) holds columns 2 q4, 2 q4 + 1 of row rho
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -474,6 +603,44 @@ bool knn_gram_supported(long long n, long long q, int d, int k) {
   return d >= g_knn_gram_min_d && q >= 8 && n >= 2048 && k + KG_MARGIN <= KG_KMAX;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// (rows, d) row-major float64 matrix as a 2-D tensor map with 16-feature x 64-row boxes,
+// 128-byte swizzle, zero fill outside the matrix
+static bool make_operand_map(CUtensorMap* map, const double* base, long long rows, int d) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)d * sizeof(double)};
+  const cuuint32_t box[2] = {KG_TF, KG_Q};
+  const cuuint32_t estride[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride,
+             box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static const int g_knn_tma_off = getenv("MGP_KNN_NO_TMA") != nullptr;  // dev switch
+
 static int gram_kk(long long n, int k, bool has_self) {
   long long kk = k + KG_MARGIN;
   const long long avail = n - (has_self ? 1 : 0);
@@ -504,20 +671,38 @@ int launch_knn_gram(const double* train, long long n, const double* queries, lon
   const bool vec = d % 2 == 0 && (uintptr_t)train % 16 == 0 && (uintptr_t)queries % 16 == 0;
   // 16-bit in-slice rows (10 instead of 12 bytes per heap entry) whenever a slice is short enough
   const bool short_rows = split_len <= 65536;
-  const size_t kg_smem =
-      2 * 2 * KG_Q * KG_LD * sizeof(double) + (size_t)kk * KG_Q * (short_rows ? 10 : 12);
-#define MGP_KG_LAUNCH(VEC_, IDX_)                                                              \
+  const size_t heap_bytes = (size_t)kk * KG_Q * (short_rows ? 10 : 12);
+  size_t kg_smem = 2 * 2 * KG_Q * KG_LD * sizeof(double) + heap_bytes;
+  // TMA path: operand boxes by cp.async.bulk.tensor into a 3-deep (2 when the candidate heaps
+  // are large) ring; needs 16-byte aligned rows (d even) and at least one full box of features
+  CUtensorMap tmq, tmx;
+  memset(&tmq, 0, sizeof(tmq));
+  memset(&tmx, 0, sizeof(tmx));
+  int nst = 0;
+  if (vec && d >= KG_TF && !g_knn_tma_off && n < (1LL << 31) && q < (1LL << 31) &&
+      make_operand_map(&tmq, queries, q, d) && make_operand_map(&tmx, train, n, d)) {
+    const size_t ring = 2 * KG_Q * KG_TF * sizeof(double);  // one stage: Q box + X box
+    const size_t rest = (KG_Q * (KG_X + 1) + 1) * sizeof(double) + heap_bytes;
+    const size_t half_sm = (size_t)max_smem_optin() / 2 - 2048;  // two CTAs per SM
+    nst = (3 * ring + rest + 1024 <= half_sm) ? 3 : 2;
+    kg_smem = nst * ring + rest + 1024;  // + slack to align the ring to 1024 bytes
+  }
+#define MGP_KG_LAUNCH(VEC_, IDX_, NST_)                                                        \
   do {                                                                                         \
-    cudaFuncSetAttribute(knn_gram_filter_kernel<VEC_, IDX_>,                                   \
+    cudaFuncSetAttribute(knn_gram_filter_kernel<VEC_, IDX_, NST_>,                             \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg_smem);           \
-    knn_gram_filter_kernel<VEC_, IDX_><<<grid, 256, kg_smem, s>>>(                             \
+    knn_gram_filter_kernel<VEC_, IDX_, NST_><<<grid, 256, kg_smem, s>>>(                       \
         train, n, queries, q, d, kk, self_idx, w.xn, w.qn, split_len, ns, w.part_idx,          \
-        w.part_s, w.cand_idx, w.cand_s);                                                       \
+        w.part_s, w.cand_idx, w.cand_s, tmq, tmx);                                             \
   } while (0)
-  if (vec && short_rows) MGP_KG_LAUNCH(true, unsigned short);
-  else if (vec) MGP_KG_LAUNCH(true, int);
-  else if (short_rows) MGP_KG_LAUNCH(false, unsigned short);
-  else MGP_KG_LAUNCH(false, int);
+  if (nst == 3 && short_rows) MGP_KG_LAUNCH(true, unsigned short, 3);
+  else if (nst == 3) MGP_KG_LAUNCH(true, int, 3);
+  else if (nst == 2 && short_rows) MGP_KG_LAUNCH(true, unsigned short, 2);
+  else if (nst == 2) MGP_KG_LAUNCH(true, int, 2);
+  else if (vec && short_rows) MGP_KG_LAUNCH(true, unsigned short, 0);
+  else if (vec) MGP_KG_LAUNCH(true, int, 0);
+  else if (short_rows) MGP_KG_LAUNCH(false, unsigned short, 0);
+  else MGP_KG_LAUNCH(false, int, 0);
 #undef MGP_KG_LAUNCH
   if (ns > 1) {
     if (kk <= 48)
