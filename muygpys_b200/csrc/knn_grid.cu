@@ -130,14 +130,22 @@ __global__ void knn_grid_kernel(const GridArgs g) {
       }
     }
     // every unvisited point lies outside the block of shells <= r: lower-bound its distance
+    // The cell of a point is floor((x - origin) / h) in floating point and the edges below are
+    // origin + c h: both carry rounding errors proportional to the COORDINATE magnitude, not
+    // to the gap, so each candidate gap is reduced by an absolute slack of a few ulps of the
+    // quantities it was formed from before it may justify stopping.
     double gap = DBL_MAX;
 #pragma unroll
     for (int f = 0; f < D; ++f) {
-      if (c[f] - r > 0) gap = fmin(gap, x[f] - (g.origin[f] + (c[f] - r) * g.h));
-      if (c[f] + r < g.dims[f] - 1) gap = fmin(gap, (g.origin[f] + (c[f] + r + 1) * g.h) - x[f]);
+      const double span = fabs(x[f]) + fabs(g.origin[f]) + (double)(c[f] + r + 1) * g.h;
+      const double slack = 8.0 * DBL_EPSILON * span;
+      if (c[f] - r > 0)
+        gap = fmin(gap, x[f] - (g.origin[f] + (c[f] - r) * g.h) - slack);
+      if (c[f] + r < g.dims[f] - 1)
+        gap = fmin(gap, (g.origin[f] + (c[f] + r + 1) * g.h) - x[f] - slack);
     }
     if (gap == DBL_MAX) break;  // the whole grid has been visited
-    // guard the bound against rounding of the cell edges; stop only when strictly inside
+    // ... and stop only when the k-th distance is strictly inside
     gap = gap * (1.0 - 1e-12) - 1e-300;
     if (gap > 0.0 && worst_d < gap * gap) break;
   }

@@ -98,15 +98,29 @@ extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_
   if (rc != MGP_OK) return rc;
   cudaStream_t main_stream = (cudaStream_t)stream;
 
+  // Whatever happens after the fork, the side streams are joined back into `stream` before
+  // returning: chunks already enqueued must stay ordered before the caller's later work (torch
+  // may reuse the staging and output tensors as soon as this call returns).
+  auto join = [&]() {
+    for (int i = 0; i < 2; ++i)
+      if (cudaEventRecord(ss->join[i], ss->s[i]) == cudaSuccess)
+        cudaStreamWaitEvent(main_stream, ss->join[i], 0);
+  };
+  bool forked = false;
 #define MGP_CUDA(call)                                                                    \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \
-    MGP_REQUIRE(e_ == cudaSuccess, MGP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    if (e_ != cudaSuccess) {                                                              \
+      set_error("%s: %s", #call, cudaGetErrorString(e_));                                 \
+      if (forked) join();                                                                 \
+      return MGP_ERR_CUDA;                                                                \
+    }                                                                                     \
   } while (0)
 
   // fork: the side streams start after everything already queued on `stream`
   MGP_CUDA(cudaEventRecord(ss->fork, main_stream));
   for (int i = 0; i < 2; ++i) MGP_CUDA(cudaStreamWaitEvent(ss->s[i], ss->fork, 0));
+  forked = true;
 
   const long long wave = 12LL * sm_count();
   const std::vector<long long> bounds = chunk_bounds(p->b, wave);
@@ -138,7 +152,10 @@ extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_
     if (p->coeffs) sub.coeffs = p->coeffs + lo * k * r;
     if (p->status) sub.status = p->status + lo;
     rc = mgp_fused_posterior(&sub, ws, ws_bytes, (void*)s);
-    if (rc != MGP_OK) return rc;
+    if (rc != MGP_OK) {
+      join();
+      return rc;
+    }
     if (mean_host)
       MGP_CUDA(cudaMemcpyAsync(mean_host + lo * r, sub.mean, (size_t)rows * r * sizeof(double),
                                cudaMemcpyDeviceToHost, s));

@@ -90,6 +90,22 @@ def _ls_list(length_scale) -> list:
         return [float(length_scale)]
 
 
+def check_index_range(idx: Optional[torch.Tensor], upper: int, name: str) -> None:
+    """ValueError for an index outside [0, upper) -- what numpy's fancy indexing raises in the
+    reference (it also wraps negatives; here they are rejected).  One min/max reduction and a
+    host read, so the hot entry points only do it when MGP_CHECK_INDICES=1; the one-time
+    set-up of an objective always does."""
+    if idx is None or idx.numel() == 0:
+        return
+    lo, hi = torch.aminmax(idx)
+    lo, hi = int(lo), int(hi)
+    if lo < 0 or hi >= upper:
+        raise ValueError(f"{name} holds values in [{lo}, {hi}], valid rows are 0..{upper - 1}")
+
+
+_CHECK_INDICES = __import__("os").environ.get("MGP_CHECK_INDICES") == "1"
+
+
 def as_2d(x: torch.Tensor) -> torch.Tensor:
     """The reference treats 1-D feature arrays as (n,1) (S/neighbors.py:84-85)."""
     return x[:, None] if x.dim() == 1 else x
@@ -158,6 +174,9 @@ def fused_posterior(
         y2 = y2.contiguous()
         r = y2.shape[1]
     dev = train_x.device
+    if _CHECK_INDICES and _host is None:
+        check_index_range(nn_idx, n, "nn_indices")
+        check_index_range(query_idx, t, "indices")
     ls = _ls_list(length_scale)
     ls_host = _host_doubles(ls)
     noise_bk = None
@@ -260,6 +279,8 @@ class FusedLoo:
         b, k = self.nn.shape
         if self.y.shape[1] != 1:
             raise NotImplementedError("mgp_fused_loo handles one response (r == 1)")
+        check_index_range(self.nn, n, "batch_nn_indices")
+        check_index_range(self.bi, n, "batch_indices")
         dev = self.x.device
         self.ls_host = (C.c_double * max(d, 1))()
         # The record is written by the kernel's last block.  By default it lives in page-locked
@@ -436,17 +457,33 @@ class KnnGrid:
         lo = train.min(dim=0).values
         hi = train.max(dim=0).values
         extent = (hi - lo).clamp_min(0.0).cpu().tolist()
-        span = [e for e in extent if e > 0.0]
         cells = min(max(n / self.POINTS_PER_CELL, 1.0), float(self.MAX_CELLS))
-        if span:
+        # cell edge from the volume of the axes that are wider than a cell; an axis that is
+        # (nearly) degenerate -- a constant feature, or one with a tiny extent next to the
+        # others -- collapses to a single layer instead of blowing the other axes' cell counts up
+        span = sorted((e for e in extent if e > 0.0), reverse=True)
+        h = 1.0
+        while span:
             volume = 1.0
             for e in span:
                 volume *= e
             h = (volume / cells) ** (1.0 / len(span))
-        else:
-            h = 1.0
+            if span[-1] >= h:
+                break
+            span.pop()  # thinner than a cell: treat as collapsed and recompute
         self.h = float(h)
         self.dims = [max(1, int(e / self.h) + 1) for e in extent]
+        ncells = 1
+        for v in self.dims:
+            ncells *= v
+        while ncells > self.MAX_CELLS:  # rounding up per axis can overshoot the cap
+            self.h *= 1.1
+            self.dims = [max(1, int(e / self.h) + 1) for e in extent]
+            ncells = 1
+            for v in self.dims:
+                ncells *= v
+        if max(self.dims) >= 2 ** 31 or ncells >= 2 ** 31:
+            raise ValueError(f"grid of {self.dims} cells does not fit 32-bit cell ids")
         self.origin = [float(v) for v in lo.cpu().tolist()]
         self._dims_c = (C.c_int32 * d)(*self.dims)
         self._origin_c = (C.c_double * d)(*self.origin)

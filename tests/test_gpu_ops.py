@@ -647,3 +647,52 @@ def test_fused_loo_record_matches_two_pass_path(loss_id, k, d):
         np.testing.assert_array_equal(again, rec)
     other = loo.record(loo.launch(ls * 1.5, noise * 2))
     assert other[L.P_SQERR] != rec[L.P_SQERR]
+
+
+def test_grid_knn_with_a_nearly_degenerate_axis_and_bad_indices():
+    """r1 advisor findings: (1) a feature that is constant up to rounding must not blow up the
+    cell grid (it collapses to one layer) and the search stays bit-identical to brute force;
+    (2) out-of-range neighbour indices are a ValueError where the objective is set up (and in
+    every fused call under MGP_CHECK_INDICES=1), not an out-of-bounds read."""
+    from muygpys_b200 import _lib as L
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(12)
+    n, q, k = 20000, 500, 20
+    x = rng.uniform(size=(n, 3))
+    x[:, 1] = 0.5 + 1e-13 * rng.normal(size=n)      # degenerate up to rounding
+    x[:, 2] *= 1e-9                                  # thin, but genuinely spread
+    qs = x[rng.choice(n, q, replace=False)] + 1e-12
+    grid = ops.KnnGrid(dev(x))
+    ncells = int(np.prod(grid.dims))
+    assert ncells <= ops.KnnGrid.MAX_CELLS and max(grid.dims) < 2 ** 31
+    idx, d2 = grid.query(dev(qs), k)
+    want_idx, want_d2 = O.knn_exact(x, qs, k)
+    np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
+    np.testing.assert_array_equal(d2.cpu().numpy(), want_d2)
+    # duplicate-heavy data far from the origin, points sitting on cell edges
+    base = 1.0e6 + np.round(rng.uniform(size=(400, 2)) * 64) / 64
+    x2 = np.repeat(base, 25, axis=0)
+    q2 = base[:200]
+    idx2, d22 = ops.KnnGrid(dev(x2)).query(dev(q2), 30)
+    want_idx2, want_d22 = O.knn_exact(x2, q2, 30)
+    np.testing.assert_array_equal(idx2.cpu().numpy(), want_idx2)
+    np.testing.assert_array_equal(d22.cpu().numpy(), want_d22)
+    # index validation
+    xs, ys = dev(rng.uniform(size=(500, 2))), dev(rng.normal(size=500))
+    bi = dev(np.arange(40))
+    nn = torch.randint(0, 500, (40, 20), device="cuda")
+    nn[3, 4] = 500
+    with pytest.raises(ValueError, match="batch_nn_indices"):
+        ops.FusedLoo(xs, ys, bi, nn, kernel_id=2, metric_id=0, loss_id=L.LOSS_MSE)
+    nn[3, 4] = -1
+    with pytest.raises(ValueError, match="batch_nn_indices"):
+        ops.FusedLoo(xs, ys, bi, nn, kernel_id=2, metric_id=0, loss_id=L.LOSS_MSE)
+    old = ops._CHECK_INDICES
+    ops._CHECK_INDICES = True
+    try:
+        with pytest.raises(ValueError, match="nn_indices"):
+            ops.fused_posterior(xs, xs, bi, nn, ys, kernel_id=2, metric_id=0, length_scale=0.2,
+                                noise=1e-3)
+    finally:
+        ops._CHECK_INDICES = old
