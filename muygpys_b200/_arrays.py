@@ -44,8 +44,24 @@ def idev(x):
     return to_dev(x, i64)
 
 
+def _is_f32(a) -> bool:
+    return (isinstance(a, np.ndarray) and a.dtype == np.float32) or (
+        isinstance(a, torch.Tensor) and a.dtype == torch.float32)
+
+
 def like_input(result: torch.Tensor, *inputs):
-    """Return `result` as numpy when the caller handed us host arrays."""
+    """Return `result` as numpy when the caller handed us host arrays.
+
+    fp32 I/O mode (the counterpart of the reference's MUYGPYS_FTYPE=32,
+    S/_src/math/numpy.py:92): when the caller's FEATURE / TARGET arrays are float32, floating
+    results come back as float32.  The kernels always compute in fp64 on the (exactly) widened
+    values, so the mode costs nothing in accuracy beyond the rounding of the inputs themselves
+    and halves the bytes that cross the host link."""
+    floats = [a for a in inputs if isinstance(a, (np.ndarray, torch.Tensor))
+              and (a.dtype in (np.float32, np.float64) if isinstance(a, np.ndarray)
+                   else a.dtype in (torch.float32, torch.float64))]
+    if result.dtype == f64 and floats and all(_is_f32(a) for a in floats):
+        result = result.to(torch.float32)
     if any(isinstance(a, np.ndarray) for a in inputs):
         return result.cpu().numpy()
     return result

@@ -31,7 +31,7 @@ static int col_formula(const Model& model) {
 }
 
 int fused_col_supported(const mgp_problem* p, const Model& model) {
-  if (p->r != 1 || p->d > 3 || p->noise_bk || p->coeffs || !p->train_y) return 0;
+  if (p->r != 1 || p->d > 3 || p->noise_bk || !p->train_y) return 0;
   const int T = col_tiles(p->k);
   if (T < 2 || T > COL_MAX_T) return 0;
   if (col_formula(model) < 0) return 0;
@@ -42,7 +42,7 @@ int fused_col_supported(const mgp_problem* p, const Model& model) {
 
 static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& loo, int* grid_out,
                       cudaStream_t stream) {
-  if (loo.grad != nullptr) {
+  if (loo.grad != nullptr || loo.backsub) {
     switch (col_formula(model)) {
       case F_M05: return launch_fused_colg_f0(p, model, loo, grid_out, stream);
       case F_M15: return launch_fused_colg_f1(p, model, loo, grid_out, stream);
@@ -66,6 +66,7 @@ static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& lo
 
 int launch_fused_col(const mgp_problem* p, const Model& model, cudaStream_t stream) {
   ColLoo loo = {};
+  loo.backsub = p->coeffs != nullptr;  // coefficients come from the back substitution
   return launch_col(p, model, loo, nullptr, stream);
 }
 

@@ -30,7 +30,9 @@
 // value with 8 T - 9 <= k <= 8 T - 2.
 //
 // Restrictions (everything else takes fused_tile / fused_generic): r == 1, d <= 3, homoscedastic
-// nugget, no coefficient output, T <= 8, covariance formula in {M05, M15, M25, GAUSS}.
+// nugget, T <= 8, covariance formula in {M05, M15, M25, GAUSS}.  The GRAD instantiations add a
+// back substitution on the stored factor (w = K^-1 kcross, alpha = K^-1 y): the analytic
+// gradient of the objective and the fast-mean coefficient output come from it.
 #pragma once
 
 #include <type_traits>
@@ -45,6 +47,7 @@ struct ColLoo {
   double* warp_rec;        // (grid, record length) per-block partial records, or NULL
   double* partials;        // (MGP_PARTIALS) final record, written by the last CTA
   double* grad;            // (MGP_GRAD_DOUBLES) gradient sums (gradient kernels only)
+  int backsub;             // use the kernels with the back substitution (gradient, coefficients)
   double inv_len[3];       // 1 / l_f of the features (gradient kernels only)
   unsigned int* counter;   // arrival counter (self-resetting)
   int loss_id;
@@ -614,6 +617,11 @@ __global__ void __launch_bounds__(COL_WARPS * 32, GRAD ? 3 : MGP_COL_MINB)
         }
       }
       __syncwarp();
+      // fast-mean precompute mode: alpha = (K + eps)^-1 y IS the coefficient row
+      // (S/_src/gp/muygps/numpy.py:88-95)
+      if (a.coeffs)
+        for (int e = lane; e < k; e += 32) a.coeffs[row * k + e] = ok ? av[e] : nan;
+      if (loo.grad != nullptr) {
       // weighted re-evaluation: per tile row I the row-factored sums
       //   Ra_f = sum_j phi z_f^2 alpha_j,  Rw_f = sum_j phi z_f^2 w_j   (j over tile columns <= I)
       // fold into  w^T dK alpha, w^T dK w, alpha^T dK alpha  (diagonal tiles count pairs twice)
@@ -708,6 +716,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32, GRAD ? 3 : MGP_COL_MINB)
       gdm[3] = -warp_sum(dwa);
       gdv[3] = warp_sum(dww);
       gdy[3] = -warp_sum(daa);
+      }
     }
 
     // ---- outputs -----------------------------------------------------------------------

@@ -388,3 +388,37 @@ def test_host_buffer_pipeline_error_behaviour():
     torch.cuda.synchronize()
     want = ops.fused_posterior(x, q, None, nn.cuda(), y, **kw)
     assert torch.equal(out["mean"], want["mean"]) and torch.equal(out["var"], want["var"])
+
+
+def test_fp32_io_mode():
+    """Optional fp32 mode (north_star: 1e-4): float32 features / targets in, float32 posterior
+    out, fp64 arithmetic inside.  Equal to the fp64 path on the fp32-rounded inputs (up to the
+    final rounding to float32) and within 1e-4 of the fp64 reference on the original inputs."""
+    from muygpys_b200.examples.from_indices import regress_from_indices
+    from muygpys_b200.examples.regress import regress_any
+    from muygpys_b200.neighbors import NN_Wrapper
+
+    case = by_name("c2_m15_2d")
+    g = load_golden(case.name)
+    data = make_data(case)
+    x64, q64, y64 = data["train_x"], data["test_x"], data["train_y"][:, 0]
+    x32, q32, y32 = (a.astype(np.float32) for a in (x64, q64, y64))
+    scale = _mods()["FixedScale"]()
+    scale._set(float(g["scale_val"]))
+    muygps = build_model(case, scale=scale)
+    nn = g["test_nn_idx"]
+    t_idx = np.arange(case.t)
+    m32, v32 = regress_from_indices(muygps, t_idx, nn, q32, x32, y32)
+    assert m32.dtype == np.float32 and v32.dtype == np.float32
+    m64, v64 = regress_from_indices(muygps, t_idx, nn, q32.astype(np.float64),
+                                    x32.astype(np.float64), y32.astype(np.float64))
+    assert m64.dtype == np.float64
+    np.testing.assert_allclose(m32, m64.astype(np.float32), rtol=0, atol=0)
+    np.testing.assert_allclose(v32, v64.astype(np.float32), rtol=0, atol=0)
+    assert_close(m32.astype(np.float64), g["mean"], 1e-4, "fp32-mode mean vs fp64 reference")
+    assert_close(v32.astype(np.float64), g["var"], 1e-4, "fp32-mode variance vs fp64 reference")
+    # device tensors: float32 in, float32 out
+    dm, dv, _ = regress_any(muygps, torch.as_tensor(q32).cuda(), torch.as_tensor(x32).cuda(),
+                            NN_Wrapper(torch.as_tensor(x32).cuda(), case.k),
+                            torch.as_tensor(y32).cuda())
+    assert dm.dtype == torch.float32 and dv.dtype == torch.float32 and dm.is_cuda
