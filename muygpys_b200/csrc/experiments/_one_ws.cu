@@ -1,0 +1,24 @@
+// dev harness: one instantiation of the warp-specialised kernel behind a C entry point
+#include "fused_ws.cuh"  // builds with -I.. from csrc/experiments
+#include <stdarg.h>
+namespace mgp {
+static char g_err2[256];
+void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err2, 256, fmt, ap); va_end(ap); }
+int check_launch(const char* w) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { set_error("%s: %s", w, cudaGetErrorString(e)); return -3; } return 0; }
+int sm_count() { return 148; }
+int max_smem_optin() { return 227 * 1024; }
+}
+extern "C" const char* one_err() { return mgp::g_err2; }
+extern "C" int one_slots() { return mgp::ws_make_slots<7>().count; }
+extern "C" int one_run(const double* x, const double* q, const int64_t* nn, const double* y, long long n,
+                       long long b, int k, double ls, double noise, double* mean, double* var, void* stream) {
+  using namespace mgp;
+  mgp_problem p = {};
+  p.train_x = x; p.query_x = q; p.nn_idx = nn; p.train_y = y; p.n = n; p.t = b; p.b = b; p.k = k; p.d = 2; p.r = 1;
+  p.kernel_id = MGP_KERNEL_MATERN_15; p.metric_id = MGP_METRIC_L2; p.length_scale_count = 1; p.length_scale = &ls;
+  p.noise = noise; p.scale = 1.0; p.mean = mean; p.var = var;
+  Model m = {}; m.kernel_id = p.kernel_id; m.metric_id = 0; m.d = 2; m.inv_ls = 1.0 / ls;
+  TileArgs a; fill_tile_args(&p, m, a);
+  ColLoo loo = {}; loo.peers.world = 1;
+  return launch_ws_one<7, 1, 2>(a, loo, b, nullptr, (cudaStream_t)stream);
+}

@@ -1,0 +1,588 @@
+// K1 (thread-per-tile variant of the column-direct kernel).
+//
+// fused_col_kernel spends 39 % of its instructions in the 52 in-tile LDL^T column steps of a
+// neighbourhood: lane-parallel steps (five 64-bit shuffles, a reciprocal, selects, six FP64
+// instructions: ~35 instructions per step) that use ~10 % of their FP64 lanes.  Here a CTA holds
+// TP_UWARPS update warps (one neighbourhood each) and ONE factor warp:
+//
+//   * update warp: gather, evaluate the covariance entries of tile column J into accumulator
+//     fragments, DMMA-update them with the finished tile columns, park the updated DIAGONAL tile
+//     in 512 bytes of shared memory, go on with the tiles below the diagonal (which do not depend
+//     on the factorisation), then pick up M_J = L_JJ^-T (B-fragment order) and -1/d and finish
+//     the column with two DMMAs per tile;
+//   * factor warp: lane g factorises the diagonal tile of update warp g ENTIRELY IN ITS OWN
+//     REGISTERS -- 8x8 LDL^T (84 FMAs, 28 multiplies, 8 reciprocals) and M = L^-T (56 FMAs) on
+//     compile-time register indices, no shuffles, no selects: ~250 instructions for
+//     TP_UWARPS tiles instead of 8 x 35 per tile.  Same operations in the same order as the
+//     lane-parallel steps of fused_col_kernel: results are bit-identical.
+//
+// Hand-offs use two named barriers (bar.arrive / bar.sync over the whole CTA).  Finished tiles
+// live in a shared-memory store whose slots are REUSED once a tile row is complete (15 instead
+// of 21 slots at T = 7).
+//
+// Same numerics, layout and restrictions as fused_col_kernel (r == 1, d <= 3, 7 <= k <= 62,
+// homoscedastic nugget, no coefficient output, no gradient).
+#pragma once
+
+#include "fused_col.cuh"
+
+namespace mgp {
+namespace {
+
+#ifndef MGP_TP_UWARPS
+#define MGP_TP_UWARPS 8
+#endif
+#ifndef MGP_TP_MINB
+#define MGP_TP_MINB 2
+#endif
+constexpr int TP_UWARPS = MGP_TP_UWARPS;
+constexpr int TP_THREADS = (TP_UWARPS + 1) * 32;
+
+// ---- shared-memory slots of the finished tiles, reused over the factorisation --------------
+// Tile (I,P), I > P, is written at the end of tile column P and last read during the update of
+// tile column I.  The tiles of the LAST tile row also park the compactly evaluated raw entries
+// from the start of the neighbourhood: they keep fixed slots 0 .. T-2.  Every other tile takes
+// the lowest slot whose previous occupant (I', P') has I' <= P.
+template <int T>
+struct TpSlots {
+  int s[T > 0 ? T : 1][T > 0 ? T : 1];
+  int count;
+};
+
+template <int T>
+constexpr TpSlots<T> tp_make_slots() {
+  TpSlots<T> m{};
+  int busy_until[T * T + 1] = {};  // slot -> tile row of its occupant (free again when <= P)
+  int count = T - 1;
+  for (int P = 0; P + 1 < T; ++P) m.s[T - 1][P] = P;
+  for (int i = 0; i < T - 1; ++i) busy_until[i] = T;  // never free
+  for (int P = 0; P + 2 < T; ++P) {
+    for (int I = P + 1; I <= T - 2; ++I) {
+      int slot = T - 1;
+      while (slot < count && busy_until[slot] > P) ++slot;
+      if (slot == count) ++count;
+      busy_until[slot] = I;
+      m.s[I][P] = slot;
+    }
+  }
+  m.count = count;
+  return m;
+}
+
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// per update warp, in doubles: finished tiles | -1/d | diagonal tile in | M out | outputs
+// (three Schur entries, ok) | 2 x points | 2 x targets; the stride is 2 (mod 16) doubles so that
+// the factor warp's lanes, which read one tile each, start in different banks
+template <int T>
+static inline size_t tp_warp_doubles(int k, int d) {
+  constexpr TpSlots<T> SL = tp_make_slots<T>();
+  const size_t pts = (size_t)((((k + 1) * d) + 1) & ~1);
+  const size_t ys = (size_t)((k + 2) & ~1);
+  size_t n = (size_t)SL.count * 64 + 8 * (size_t)T + 64 + 64 + 8 + 2 * pts + 2 * ys;
+  while ((n & 15) != 2) n += 2;
+  return n;
+}
+
+// One lane: LDL^T of the first `ncols` columns of an 8x8 symmetric tile (row-major at xin,
+// lower triangle significant) and M = L^-T, the product of the column operations.
+//   dinv[c]      = -1/d_c (eliminated columns), -0 otherwise
+//   xout[8 c + r] = M[r][c] for r < c  (M is unit upper triangular; the diagonal and the zeros
+//                   below it are preset once per kernel) -- the B-fragment order of the DMMAs
+//   xo[0..2]     = entries (n,n), (n+1,n), (n+1,n+1) of the partially eliminated tile, n = ncols
+//   xo[3]        = 1 if every pivot was positive, finite and normal
+__device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
+                                               double* __restrict__ xout,
+                                               double* __restrict__ dinv,
+                                               double* __restrict__ xo, int ncols) {
+  double a[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; j += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(xin + 8 * i + j);
+      a[i][j] = t.x;
+      if (j + 1 <= i) a[i][j + 1] = t.y;
+    }
+  }
+  double v[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[r][c] = 0.0;
+  double nd[8];
+  double cap0 = 0.0, cap1 = 0.0, cap2 = 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    nd[j] = -0.0;
+    if (j < ncols) {
+      const double p = a[j][j];
+      ok = ok && ((unsigned)(__double2hiint(p) - 1) < 0x7fefffffu);
+      const double pinv = rcp_fast(p);
+      nd[j] = -pinv;
+      double l[8];
+#pragma unroll
+      for (int c = j + 1; c < 8; ++c) l[c] = a[c][j] * pinv;
+#pragma unroll
+      for (int c = j + 1; c < 8; ++c) {
+#pragma unroll
+        for (int i = c; i < 8; ++i) a[i][c] = fma(-a[i][j], l[c], a[i][c]);
+      }
+#pragma unroll
+      for (int c = j + 1; c < 8; ++c) {
+#pragma unroll
+        for (int r = 0; r < j; ++r) v[r][c] = fma(-v[r][j], l[c], v[r][c]);
+        v[j][c] = -l[c];
+      }
+    } else if (j == ncols) {
+      cap0 = a[j][j];
+      if (j < 7) {
+        cap1 = a[j + 1][j];
+        cap2 = a[j + 1][j + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; c += 2)
+    *reinterpret_cast<double2*>(dinv + c) = make_double2(nd[c], nd[c + 1]);
+#pragma unroll
+  for (int c = 1; c < 8; ++c) {
+#pragma unroll
+    for (int r = 0; r < c; r += 2) {
+      const double lo = v[r][c];
+      const double hi = (r + 1 == c) ? 1.0 : ((r + 1 > c) ? 0.0 : v[r + 1][c]);
+      *reinterpret_cast<double2*>(xout + 8 * c + r) = make_double2(lo, hi);
+    }
+  }
+  *reinterpret_cast<double2*>(xo) = make_double2(cap0, cap1);
+  *reinterpret_cast<double2*>(xo + 2) = make_double2(cap2, ok ? 1.0 : 0.0);
+}
+
+template <int T, int F, int D>
+__global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
+    fused_tp_kernel(const TileArgs a, const ColLoo loo, int pts_doubles, int ys_doubles,
+                    int warp_doubles, long long iters) {
+  extern __shared__ double smem[];
+  constexpr TpSlots<T> SL = tp_make_slots<T>();
+  constexpr int W = 8 * (T - 1);
+  constexpr int NREC = MGP_PARTIALS;
+  __shared__ double s_acc[TP_UWARPS][NREC];
+  for (int e = threadIdx.x; e < TP_UWARPS * NREC; e += blockDim.x) (&s_acc[0][0])[e] = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rho = lane >> 2, q = lane & 3, qb = lane & ~3;
+  const int k = a.k;
+  const int nel = k + 1 - W;
+  const int kl = k & 7;
+  auto warp_base = [&](int u) { return smem + (size_t)u * warp_doubles; };
+  constexpr int OFF_DINV = SL.count * 64, OFF_XIN = OFF_DINV + 8 * T, OFF_XOUT = OFF_XIN + 64,
+                OFF_XO = OFF_XOUT + 64, OFF_PTS = OFF_XO + 8;
+
+  // M is unit upper triangular: its diagonal and the zeros below it never change
+  if (warp < TP_UWARPS) {
+    double* xout = warp_base(warp) + OFF_XOUT;
+    for (int e = lane; e < 64; e += 32) xout[e] = ((e >> 3) == (e & 7)) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  if (warp >= TP_UWARPS) {
+    // =================================== factor warp ========================================
+    // lane g < TP_UWARPS owns the diagonal tile of update warp g: the whole 8x8 LDL^T and
+    // M = L^-T run in that lane's registers (no shuffles, no selects)
+    double* base = warp_base(lane < TP_UWARPS ? lane : 0);
+    for (long long it = 0; it < iters; ++it) {
+      for (int J = 0; J < T; ++J) {
+        const int ncols = (J <= T - 3) ? 8 : max(0, min(8, k - 8 * J));
+        bar_sync(1, TP_THREADS);  // every update warp has parked its updated diagonal tile
+        if (lane < TP_UWARPS)
+          tp_factor_tile(base + OFF_XIN, base + OFF_XOUT, base + OFF_DINV + 8 * J, base + OFF_XO,
+                         ncols);
+        bar_arrive(2, TP_THREADS);
+      }
+    }
+  } else {
+    // =================================== update warp ========================================
+    const double tab64 = a.exp_tab[lane];
+    double* Ls = warp_base(warp);
+    double* dinv_s = Ls + OFF_DINV;
+    double* Xin = Ls + OFF_XIN;
+    const double* Xout = Ls + OFF_XOUT;
+    const double* xo = Ls + OFF_XO;
+    double* pts_buf = Ls + OFF_PTS;
+    double* ys_buf = pts_buf + 2 * pts_doubles;
+    const long long wglobal = (long long)blockIdx.x * TP_UWARPS + warp;
+    const long long wstride = (long long)gridDim.x * TP_UWARPS;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double onep = 1.0 + a.noise;
+    const long long last = a.b - 1;
+
+    // rows beyond the batch repeat the last row (the pair and its factor warp stay in step)
+    auto load_src = [&](long long row, int i) -> long long {
+      if (i > k) return -1;
+      const long long rr = row < a.b ? row : last;
+      if (i == k) return a.query_idx ? a.query_idx[rr] : rr;
+      return a.nn_idx[rr * k + i];
+    };
+    auto issue_rows = [&](int buf, int i, long long src) {
+      if (src < 0) return;
+      const double* px = ((i == k) ? a.query_x : a.train_x) + src * D;
+      double* dst = pts_buf + buf * pts_doubles + i * D;
+      if (D == 2) {
+        cp_async16(dst, px);
+      } else {
+#pragma unroll
+        for (int f = 0; f < D; ++f) cp_async8(dst + f, px + f);
+      }
+      if (i < k) cp_async8(ys_buf + buf * ys_doubles + i, a.train_y + src);
+    };
+
+    long long s0 = load_src(wglobal, lane), s1 = load_src(wglobal, lane + 32);
+    long long q_src = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);
+    issue_rows(0, lane, s0);
+    issue_rows(0, lane + 32, s1);
+    cp_async_commit();
+    s0 = load_src(wglobal + wstride, lane);
+    s1 = load_src(wglobal + wstride, lane + 32);
+
+    int buf = 0;
+    for (long long it = 0; it < iters; ++it, buf ^= 1) {
+      const long long row = wglobal + it * wstride;
+      const bool live = row < a.b;
+      cp_async_wait_all();
+      __syncwarp();
+      const long long q_next = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);
+      issue_rows(buf ^ 1, lane, s0);
+      issue_rows(buf ^ 1, lane + 32, s1);
+      cp_async_commit();
+      s0 = load_src(row + 2 * wstride, lane);
+      s1 = load_src(row + 2 * wstride, lane + 32);
+      double* pts = pts_buf + buf * pts_doubles;
+      const double* ys = ys_buf + buf * ys_doubles;
+      if (D == 2) {
+        double2* p2 = reinterpret_cast<double2*>(pts);
+        for (int i = lane; i <= k; i += 32) {
+          double2 v = p2[i];
+          v.x *= a.coord_scale[0];
+          v.y *= a.coord_scale[1];
+          p2[i] = v;
+        }
+      } else {
+        for (int e = lane; e < (k + 1) * D; e += 32) pts[e] *= a.coord_scale[e % D];
+      }
+      __syncwarp();
+
+      // compact evaluation of the real rows of the last tile row (columns < W)
+      if (T > 1) {
+        const int total = nel * W;
+        auto chunk = [&](int base, auto nway) {
+          constexpr int N = decltype(nway)::value;
+          double u[N], o[N];
+          int dst[N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const int e = base + 32 * i + lane;
+            const int ee = e < total ? e : 0;
+            const int ar = ee / W, j = ee - ar * W;
+            u[i] = sq_dist<D>(ld_pt<D>(pts, W + ar), ld_pt<D>(pts, j));
+            dst[i] = e < total ? (j >> 3) * 64 + ar * 8 + (j & 7) : -1;  // slot of (T-1, j/8)
+          }
+          cov_n<F, N>(u, tab64, o);
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            if (dst[i] >= 0) Ls[dst[i]] = o[i];
+        };
+        int base = 0;
+        for (; base + 64 < total; base += 96) chunk(base, std::integral_constant<int, 3>());
+        if (base + 32 < total) chunk(base, std::integral_constant<int, 2>());
+        else if (base < total) chunk(base, std::integral_constant<int, 1>());
+        __syncwarp();
+      }
+
+      bool ok = true;
+      double out_var = 0.0, out_mean = 0.0, out_yky = 0.0;
+#pragma unroll
+      for (int J = 0; J < T; ++J) {
+        double c[T][2];
+        const int j0 = 8 * J + 2 * q, j1 = j0 + 1;
+        const Pt<D> pc0 = ld_pt<D>(pts, (J == T - 1) ? min(j0, k) : j0);
+        const Pt<D> pc1 = ld_pt<D>(pts, (J == T - 1) ? min(j1, k) : j1);
+        double b0[T], b1[T];
+        double2 ljs[T];
+#pragma unroll
+        for (int P = 0; P < J; ++P) {
+          ljs[P] = *reinterpret_cast<const double2*>(Ls + SL.s[J][P] * 64 + 2 * lane);
+          const double2 nd = *reinterpret_cast<const double2*>(dinv_s + 8 * P + 2 * q);
+          b0[P] = ljs[P].x * nd.x;
+          b1[P] = ljs[P].y * nd.y;
+        }
+        auto fix_diag = [&](int I) {
+          const double dg = (8 * I + rho < k) ? onep : 1.0;
+          c[I][0] = (rho == 2 * q) ? dg : c[I][0];
+          c[I][1] = (rho == 2 * q + 1) ? dg : c[I][1];
+        };
+        auto eval_two = [&](int Ia, int Ib) {
+          const Pt<D> pa = ld_pt<D>(pts, 8 * Ia + rho), pb = ld_pt<D>(pts, 8 * Ib + rho);
+          const double u[4] = {sq_dist<D>(pa, pc0), sq_dist<D>(pa, pc1), sq_dist<D>(pb, pc0),
+                               sq_dist<D>(pb, pc1)};
+          double o[4];
+          cov_n<F, 4>(u, tab64, o);
+          c[Ia][0] = o[0];
+          c[Ia][1] = o[1];
+          c[Ib][0] = o[2];
+          c[Ib][1] = o[3];
+          if (Ia == J) fix_diag(Ia);
+        };
+        auto eval_one = [&](int Ia) {
+          const Pt<D> pa = ld_pt<D>(pts, 8 * Ia + rho);
+          const double u[2] = {sq_dist<D>(pa, pc0), sq_dist<D>(pa, pc1)};
+          double o[2];
+          cov_n<F, 2>(u, tab64, o);
+          c[Ia][0] = o[0];
+          c[Ia][1] = o[1];
+          if (Ia == J) fix_diag(Ia);
+        };
+        auto load_last = [&]() {
+          const double2 v = *reinterpret_cast<const double2*>(Ls + SL.s[T - 1][J] * 64 + 2 * lane);
+          const double2 yv = *reinterpret_cast<const double2*>(ys + j0);
+          const bool isy = rho == nel;
+          const double y0 = (isy && j0 < k) ? yv.x : 0.0, y1 = (isy && j1 < k) ? yv.y : 0.0;
+          c[T - 1][0] = (rho < nel) ? v.x : y0;
+          c[T - 1][1] = (rho < nel) ? v.y : y1;
+        };
+        auto eval_corner = [&]() {
+          const int i = W + rho;
+          const Pt<D> pr = ld_pt<D>(pts, min(i, k));
+          const double u[2] = {sq_dist<D>(pr, pc0), sq_dist<D>(pr, pc1)};
+          double o[2];
+          cov_n<F, 2>(u, tab64, o);
+          const double y0 = ys[min(j0, k)], y1 = ys[min(j1, k)];
+          const double dg = (i < k) ? onep : 1.0;
+          const bool krow = i <= k, yrow = i == k + 1;
+          double r0 = (krow && j0 < k) ? o[0] : ((yrow && j0 < k) ? y0 : 0.0);
+          double r1 = (krow && j1 < k) ? o[1] : ((yrow && j1 < k) ? y1 : 0.0);
+          r0 = (krow && i == j0) ? dg : r0;
+          r1 = (krow && i == j1) ? dg : r1;
+          c[T - 1][0] = r0;
+          c[T - 1][1] = r1;
+        };
+        auto frag = [&](int I, int P) -> double2 {
+          return (I == J) ? ljs[P]
+                          : *reinterpret_cast<const double2*>(Ls + SL.s[I][P] * 64 + 2 * lane);
+        };
+        auto update_two = [&](int Ia, int Ib) {
+#pragma unroll
+          for (int P = 0; P < J; ++P) {
+            const double2 la = frag(Ia, P), lb = frag(Ib, P);
+            dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
+            dmma_free(c[Ib][0], c[Ib][1], lb.x, b0[P]);
+            dmma_free(c[Ia][0], c[Ia][1], la.y, b1[P]);
+            dmma_free(c[Ib][0], c[Ib][1], lb.y, b1[P]);
+          }
+        };
+        auto update_one = [&](int Ia) {
+          if (J >= 2) {
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int P = 0; P < J; ++P) {
+              const double2 la = frag(Ia, P);
+              dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
+              dmma_free(x0, x1, la.y, b1[P]);
+            }
+            c[Ia][0] += x0;
+            c[Ia][1] += x1;
+          } else {
+#pragma unroll
+            for (int P = 0; P < J; ++P) {
+              const double2 la = frag(Ia, P);
+              dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
+              dmma_free(c[Ia][0], c[Ia][1], la.y, b1[P]);
+            }
+          }
+        };
+        auto work_item = [&](int m) {
+          const int Ia = J + 2 + 2 * m, Ib = Ia + 1;
+          if (J > T - 3 || Ia > T - 1) return;
+          if (Ib <= T - 2) {
+            eval_two(Ia, Ib);
+            update_two(Ia, Ib);
+          } else if (Ia <= T - 2) {
+            eval_one(Ia);
+            load_last();
+            update_two(Ia, T - 1);
+          } else {
+            load_last();
+            update_one(T - 1);
+          }
+        };
+
+        if (J <= T - 3) {
+          eval_two(J, J + 1);
+          update_two(J, J + 1);
+        } else if (J == T - 2) {
+          eval_one(J);
+          load_last();
+          update_two(J, T - 1);
+        } else {
+          eval_corner();
+          update_one(J);
+        }
+        // hand the updated diagonal tile to the factor warp ...
+        *reinterpret_cast<double2*>(Xin + 2 * lane) = make_double2(c[J][0], c[J][1]);
+        bar_arrive(1, TP_THREADS);
+        // ... and go on with the tiles below the diagonal, which do not depend on it
+#pragma unroll
+        for (int m = 0; m < 4; ++m) work_item(m);
+        bar_sync(2, TP_THREADS);  // M_J, 1/d and the outputs of this column are in place
+        ok = ok && (xo[3] != 0.0);
+        // xo[0..2]: entries (n,n), (n+1,n), (n+1,n+1) of the tile after its n = ncols steps
+        if (J == T - 1) {
+          if (kl < 7) {
+            out_var = xo[0];
+            out_mean = -xo[1];
+            out_yky = -xo[2];
+          } else {
+            out_yky = -xo[0];
+          }
+        }
+        if (J == T - 2 && kl == 7) out_var = xo[0];
+        if (J + 1 < T) {
+          const double2 bm = *reinterpret_cast<const double2*>(Xout + 2 * lane);
+          double n0[T], n1[T];
+#pragma unroll
+          for (int I = J + 1; I < T; ++I) {
+            n0[I] = 0.0;
+            n1[I] = 0.0;
+            dmma_free(n0[I], n1[I], c[I][0], bm.x);
+          }
+#pragma unroll
+          for (int I = J + 1; I < T; ++I) {
+            dmma_free(n0[I], n1[I], c[I][1], bm.y);
+            *reinterpret_cast<double2*>(Ls + SL.s[I][J] * 64 + 2 * lane) =
+                make_double2(n0[I], n1[I]);
+          }
+          if (J == T - 2 && kl == 7) out_mean = -shfl_d(n1[T - 1], 3);
+        }
+      }
+
+      if (lane == 0 && live) {
+        if (a.var) a.var[row] = ok ? a.scale * out_var : nan;
+        if (a.mean) a.mean[row] = ok ? out_mean : nan;
+        if (a.yky) a.yky[row] = ok ? out_yky : nan;
+        if (a.status) a.status[row] = ok ? 0 : 1;
+        if (loo.warp_rec) {
+          double* acc = s_acc[warp];
+          if (ok) {
+            const double err = out_mean - a.train_y[q_src];
+            const double e2 = err * err;
+            acc[MGP_P_SQERR] += e2;
+            acc[MGP_P_COUNT] += 1.0;
+            acc[MGP_P_YKY] += out_yky;
+            acc[MGP_P_ROWS] += 1.0;
+            acc[MGP_P_SQERR_V] += e2 / out_var;
+            acc[MGP_P_LOGV] += log(out_var);
+            if (loo.loss_id == MGP_LOSS_PSEUDO_HUBER) {
+              const double z = err / loo.boundary_scale;
+              acc[MGP_P_AUX] +=
+                  loo.boundary_scale * loo.boundary_scale * (sqrt(fma(z, z, 1.0)) - 1.0);
+            }
+          } else {
+            acc[MGP_P_BAD] += 1.0;
+          }
+        }
+      }
+      q_src = q_next;
+      __syncwarp();
+    }
+    cp_async_wait_all();
+  }
+
+  if (loo.warp_rec) {
+    // fixed-order reduction, as in fused_col_kernel: update warps of a block -> block record ->
+    // (last block) strided partial sums -> sequential sum; then the cross-GPU exchange
+    __shared__ unsigned int s_last;
+    constexpr int NGRP = 16;
+    __shared__ double s_red[NGRP][NREC];
+    __syncthreads();
+    if (threadIdx.x < NREC) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < TP_UWARPS; ++w) v += s_acc[w][threadIdx.x];
+      loo.warp_rec[(size_t)blockIdx.x * NREC + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(loo.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (threadIdx.x < NGRP * NREC) {
+        const int slot = threadIdx.x % NREC, grp = threadIdx.x / NREC;
+        double sum = 0.0;
+        for (int cidx = grp; cidx < (int)gridDim.x; cidx += NGRP)
+          sum += __ldcg(loo.warp_rec + (size_t)cidx * NREC + slot);
+        s_red[grp][slot] = sum;
+      }
+      __syncthreads();
+      __shared__ double s_tot[MGP_PARTIALS];
+      if (threadIdx.x < NREC) {
+        double tot = 0.0;
+#pragma unroll
+        for (int g = 0; g < NGRP; ++g) tot += s_red[g][threadIdx.x];
+        s_tot[threadIdx.x] = tot;
+        if (loo.peers.world <= 1) loo.partials[threadIdx.x] = tot;
+      }
+      if (threadIdx.x == 0) *loo.counter = 0u;
+      if (loo.peers.world > 1) {
+        __syncthreads();
+        peer_sum8_block(loo.peers, s_tot, loo.partials);
+      }
+    }
+  }
+}
+
+template <int T, int F, int D>
+int launch_tp_one(const TileArgs& a, const ColLoo& loo, long long rows, int* grid_out,
+                  cudaStream_t stream) {
+  const int pts_doubles = (((a.k + 1) * D) + 1) & ~1;
+  const int ys_doubles = (a.k + 2) & ~1;
+  const size_t warp_doubles = tp_warp_doubles<T>(a.k, D);
+  const size_t smem = warp_doubles * TP_UWARPS * sizeof(double);
+  cudaFuncAttributes fa;
+  MGP_REQUIRE(cudaFuncGetAttributes(&fa, fused_tp_kernel<T, F, D>) == cudaSuccess, MGP_ERR_CUDA,
+              "cudaFuncGetAttributes failed");
+  const size_t smem_cap = (size_t)max_smem_optin() - fa.sharedSizeBytes;
+  MGP_REQUIRE(smem <= smem_cap, MGP_ERR_UNSUPPORTED,
+              "warp-specialised kernel shared memory %zu too large", smem);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaFuncSetAttribute(fused_tp_kernel<T, F, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem_cap);
+    attr_set[dev] = true;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_tp_kernel<T, F, D>,
+                                                    TP_THREADS, smem) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  long long blocks = (rows + TP_UWARPS - 1) / TP_UWARPS;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (grid_out) {
+    blocks = *grid_out > 0 ? *grid_out : cap;
+    *grid_out = (int)blocks;
+  }
+  const long long iters = (rows + blocks * TP_UWARPS - 1) / (blocks * TP_UWARPS);
+  fused_tp_kernel<T, F, D><<<(unsigned)blocks, TP_THREADS, smem, stream>>>(
+      a, loo, pts_doubles, ys_doubles, (int)warp_doubles, iters);
+  return check_launch("fused_tp_kernel");
+}
+
+}  // namespace
+}  // namespace mgp

@@ -14,7 +14,10 @@ ops.set_fused_variant(2)
 ref = ops.fused_posterior(x, q, None, nn, y, kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 res = {}
+only = os.environ.get("ONLY")  # comma-separated variant names
 for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "muygpys_b200", "csrc", "build", "libone_*.so"))):
+    if only and os.path.basename(path)[7:-3] not in only.split(","):
+        continue
     lib = C.CDLL(path)
     lib.one_run.argtypes = [C.c_void_p] * 4 + [C.c_longlong, C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.one_err.restype = C.c_char_p
