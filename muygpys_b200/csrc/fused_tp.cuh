@@ -249,10 +249,227 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
     s0 = load_src(wglobal + wstride, lane);
     s1 = load_src(wglobal + wstride, lane + 32);
 
+    // ---- results of one neighbourhood (called one pipeline stage after its last column) -----
+    bool ok = true;
+    double out_var = 0.0, out_mean = 0.0, out_yky = 0.0;
+    auto write_outputs = [&](long long row, long long qs) {
+      if (lane == 0 && row < a.b) {
+        if (a.var) a.var[row] = ok ? a.scale * out_var : nan;
+        if (a.mean) a.mean[row] = ok ? out_mean : nan;
+        if (a.yky) a.yky[row] = ok ? out_yky : nan;
+        if (a.status) a.status[row] = ok ? 0 : 1;
+        if (loo.warp_rec) {
+          double* acc = s_acc[warp];
+          if (ok) {
+            const double err = out_mean - a.train_y[qs];
+            const double e2 = err * err;
+            acc[MGP_P_SQERR] += e2;
+            acc[MGP_P_COUNT] += 1.0;
+            acc[MGP_P_YKY] += out_yky;
+            acc[MGP_P_ROWS] += 1.0;
+            acc[MGP_P_SQERR_V] += e2 / out_var;
+            acc[MGP_P_LOGV] += log(out_var);
+            if (loo.loss_id == MGP_LOSS_PSEUDO_HUBER) {
+              const double z = err / loo.boundary_scale;
+              acc[MGP_P_AUX] +=
+                  loo.boundary_scale * loo.boundary_scale * (sqrt(fma(z, z, 1.0)) - 1.0);
+            }
+          } else {
+            acc[MGP_P_BAD] += 1.0;
+          }
+        }
+      }
+    };
+    // pick up what the factor warp left for tile column J (after bar_sync(2))
+    auto read_factor_outputs = [&](int J) {
+      ok = ok && (xo[3] != 0.0);
+      // xo[0..2]: entries (n,n), (n+1,n), (n+1,n+1) of the tile after its n = ncols steps
+      if (J == T - 1) {
+        if (kl < 7) {
+          out_var = xo[0];
+          out_mean = -xo[1];
+          out_yky = -xo[2];
+        } else {
+          out_yky = -xo[0];
+        }
+      }
+      if (J == T - 2 && kl == 7) out_var = xo[0];
+    };
+
+    // The tile column under construction: rows J .. T-1 as accumulator fragments.
+    double c[T][2];
+
+    // Build tile column J: evaluate its entries and subtract the products with the finished tile
+    // columns P < NP.  (NP = J - 1 in the pipeline: column J - 1 is still with the factor warp;
+    // its term is added by finish_column.)
+    auto build_column = [&](int J, int NP, const double* pts, const double* ys) {
+      const int j0 = 8 * J + 2 * q, j1 = j0 + 1;
+      const Pt<D> pc0 = ld_pt<D>(pts, (J == T - 1) ? min(j0, k) : j0);
+      const Pt<D> pc1 = ld_pt<D>(pts, (J == T - 1) ? min(j1, k) : j1);
+      double b0[T], b1[T];
+      double2 ljs[T];
+#pragma unroll
+      for (int P = 0; P < NP; ++P) {
+        ljs[P] = *reinterpret_cast<const double2*>(Ls + SL.s[J][P] * 64 + 2 * lane);
+        const double2 nd = *reinterpret_cast<const double2*>(dinv_s + 8 * P + 2 * q);
+        b0[P] = ljs[P].x * nd.x;
+        b1[P] = ljs[P].y * nd.y;
+      }
+      auto fix_diag = [&](int I) {
+        const double dg = (8 * I + rho < k) ? onep : 1.0;
+        c[I][0] = (rho == 2 * q) ? dg : c[I][0];
+        c[I][1] = (rho == 2 * q + 1) ? dg : c[I][1];
+      };
+      auto eval_two = [&](int Ia, int Ib) {
+        const Pt<D> pa = ld_pt<D>(pts, 8 * Ia + rho), pb = ld_pt<D>(pts, 8 * Ib + rho);
+        const double u[4] = {sq_dist<D>(pa, pc0), sq_dist<D>(pa, pc1), sq_dist<D>(pb, pc0),
+                             sq_dist<D>(pb, pc1)};
+        double o[4];
+        cov_n<F, 4>(u, tab64, o);
+        c[Ia][0] = o[0];
+        c[Ia][1] = o[1];
+        c[Ib][0] = o[2];
+        c[Ib][1] = o[3];
+        if (Ia == J) fix_diag(Ia);
+      };
+      auto eval_one = [&](int Ia) {
+        const Pt<D> pa = ld_pt<D>(pts, 8 * Ia + rho);
+        const double u[2] = {sq_dist<D>(pa, pc0), sq_dist<D>(pa, pc1)};
+        double o[2];
+        cov_n<F, 2>(u, tab64, o);
+        c[Ia][0] = o[0];
+        c[Ia][1] = o[1];
+        if (Ia == J) fix_diag(Ia);
+      };
+      // last tile row left of its diagonal tile: parked values, target row, zero padding
+      auto load_last = [&]() {
+        const double2 v = *reinterpret_cast<const double2*>(Ls + SL.s[T - 1][J] * 64 + 2 * lane);
+        const double2 yv = *reinterpret_cast<const double2*>(ys + j0);
+        const bool isy = rho == nel;
+        const double y0 = (isy && j0 < k) ? yv.x : 0.0, y1 = (isy && j1 < k) ? yv.y : 0.0;
+        c[T - 1][0] = (rho < nel) ? v.x : y0;
+        c[T - 1][1] = (rho < nel) ? v.y : y1;
+      };
+      // last diagonal tile: every kind of entry, masked
+      auto eval_corner = [&]() {
+        const int i = W + rho;
+        const Pt<D> pr = ld_pt<D>(pts, min(i, k));
+        const double u[2] = {sq_dist<D>(pr, pc0), sq_dist<D>(pr, pc1)};
+        double o[2];
+        cov_n<F, 2>(u, tab64, o);
+        const double y0 = ys[min(j0, k)], y1 = ys[min(j1, k)];
+        const double dg = (i < k) ? onep : 1.0;
+        const bool krow = i <= k, yrow = i == k + 1;
+        double r0 = (krow && j0 < k) ? o[0] : ((yrow && j0 < k) ? y0 : 0.0);
+        double r1 = (krow && j1 < k) ? o[1] : ((yrow && j1 < k) ? y1 : 0.0);
+        r0 = (krow && i == j0) ? dg : r0;
+        r1 = (krow && i == j1) ? dg : r1;
+        c[T - 1][0] = r0;
+        c[T - 1][1] = r1;
+      };
+      auto frag = [&](int I, int P) -> double2 {
+        return (I == J) ? ljs[P]
+                        : *reinterpret_cast<const double2*>(Ls + SL.s[I][P] * 64 + 2 * lane);
+      };
+      auto update_two = [&](int Ia, int Ib) {
+#pragma unroll
+        for (int P = 0; P < NP; ++P) {
+          const double2 la = frag(Ia, P), lb = frag(Ib, P);
+          dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
+          dmma_free(c[Ib][0], c[Ib][1], lb.x, b0[P]);
+          dmma_free(c[Ia][0], c[Ia][1], la.y, b1[P]);
+          dmma_free(c[Ib][0], c[Ib][1], lb.y, b1[P]);
+        }
+      };
+      auto update_one = [&](int Ia) {
+        if (NP >= 2) {  // two partial sums: even / odd slices
+          double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+          for (int P = 0; P < NP; ++P) {
+            const double2 la = frag(Ia, P);
+            dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
+            dmma_free(x0, x1, la.y, b1[P]);
+          }
+          c[Ia][0] += x0;
+          c[Ia][1] += x1;
+        } else {
+#pragma unroll
+          for (int P = 0; P < NP; ++P) {
+            const double2 la = frag(Ia, P);
+            dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
+            dmma_free(c[Ia][0], c[Ia][1], la.y, b1[P]);
+          }
+        }
+      };
+      // tiles in pairs: (J, J+1), (J+2, J+3), ...; the last tile row comes from load_last
+#pragma unroll
+      for (int Ia = J; Ia < T; Ia += 2) {
+        const int Ib = Ia + 1;
+        if (J == T - 1) {
+          eval_corner();
+          update_one(T - 1);
+        } else if (Ib <= T - 2) {
+          eval_two(Ia, Ib);
+          update_two(Ia, Ib);
+        } else if (Ia <= T - 2) {  // Ib == T-1
+          eval_one(Ia);
+          load_last();
+          update_two(Ia, T - 1);
+        } else {  // Ia == T-1
+          load_last();
+          update_one(T - 1);
+        }
+      }
+    };
+
+    // Column J has been built: hand its diagonal tile to the factor warp, park the tiles
+    // below it (raw) in the slots their finished versions will take.
+    auto hand_off = [&](int J) {
+      *reinterpret_cast<double2*>(Xin + 2 * lane) = make_double2(c[J][0], c[J][1]);
+      bar_arrive(1, TP_THREADS);
+#pragma unroll
+      for (int I = J + 1; I < T; ++I)
+        *reinterpret_cast<double2*>(Ls + SL.s[I][J] * 64 + 2 * lane) =
+            make_double2(c[I][0], c[I][1]);
+    };
+
+    // M_J and 1/d_J are in place: finish the tiles below the diagonal (U = S M, two DMMAs per
+    // tile) and subtract column J's term from column J + 1, which sits in c[][].
+    auto finish_column = [&](int J) {
+      if (J + 1 >= T) return;
+      const double2 bm = *reinterpret_cast<const double2*>(Xout + 2 * lane);
+      const double2 nd = *reinterpret_cast<const double2*>(dinv_s + 8 * J + 2 * q);
+      double n0[T], n1[T];
+      double2 raw[T];
+#pragma unroll
+      for (int I = J + 1; I < T; ++I)
+        raw[I] = *reinterpret_cast<const double2*>(Ls + SL.s[I][J] * 64 + 2 * lane);
+#pragma unroll
+      for (int I = J + 1; I < T; ++I) {
+        n0[I] = 0.0;
+        n1[I] = 0.0;
+        dmma_free(n0[I], n1[I], raw[I].x, bm.x);
+      }
+#pragma unroll
+      for (int I = J + 1; I < T; ++I) {
+        dmma_free(n0[I], n1[I], raw[I].y, bm.y);
+        *reinterpret_cast<double2*>(Ls + SL.s[I][J] * 64 + 2 * lane) = make_double2(n0[I], n1[I]);
+      }
+      if (J == T - 2 && kl == 7) out_mean = -shfl_d(n1[T - 1], 3);
+      const double bj0 = n0[J + 1] * nd.x, bj1 = n1[J + 1] * nd.y;
+#pragma unroll
+      for (int I = J + 1; I < T; ++I) dmma_free(c[I][0], c[I][1], n0[I], bj0);
+#pragma unroll
+      for (int I = J + 1; I < T; ++I) dmma_free(c[I][0], c[I][1], n1[I], bj1);
+    };
+
+    // Software pipeline, one stage per tile column: while the factor warp works on the
+    // diagonal tile of column J, this warp builds column J + 1 -- for J = T - 1 that is
+    // column 0 of the NEXT neighbourhood, staging and compact evaluation included.
     int buf = 0;
+    long long prev_row = 0, prev_q = 0;
     for (long long it = 0; it < iters; ++it, buf ^= 1) {
       const long long row = wglobal + it * wstride;
-      const bool live = row < a.b;
       cp_async_wait_all();
       __syncwarp();
       const long long q_next = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);
@@ -276,7 +493,9 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
       }
       __syncwarp();
 
-      // compact evaluation of the real rows of the last tile row (columns < W)
+      // compact evaluation of the real rows of the last tile row (columns < W); the slots are
+      // free: every finished tile of the previous neighbourhood was last read while its last
+      // column was built
       if (T > 1) {
         const int total = nel * W;
         auto chunk = [&](int base, auto nway) {
@@ -302,201 +521,31 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
         else if (base < total) chunk(base, std::integral_constant<int, 1>());
         __syncwarp();
       }
-
-      bool ok = true;
-      double out_var = 0.0, out_mean = 0.0, out_yky = 0.0;
-#pragma unroll
-      for (int J = 0; J < T; ++J) {
-        double c[T][2];
-        const int j0 = 8 * J + 2 * q, j1 = j0 + 1;
-        const Pt<D> pc0 = ld_pt<D>(pts, (J == T - 1) ? min(j0, k) : j0);
-        const Pt<D> pc1 = ld_pt<D>(pts, (J == T - 1) ? min(j1, k) : j1);
-        double b0[T], b1[T];
-        double2 ljs[T];
-#pragma unroll
-        for (int P = 0; P < J; ++P) {
-          ljs[P] = *reinterpret_cast<const double2*>(Ls + SL.s[J][P] * 64 + 2 * lane);
-          const double2 nd = *reinterpret_cast<const double2*>(dinv_s + 8 * P + 2 * q);
-          b0[P] = ljs[P].x * nd.x;
-          b1[P] = ljs[P].y * nd.y;
-        }
-        auto fix_diag = [&](int I) {
-          const double dg = (8 * I + rho < k) ? onep : 1.0;
-          c[I][0] = (rho == 2 * q) ? dg : c[I][0];
-          c[I][1] = (rho == 2 * q + 1) ? dg : c[I][1];
-        };
-        auto eval_two = [&](int Ia, int Ib) {
-          const Pt<D> pa = ld_pt<D>(pts, 8 * Ia + rho), pb = ld_pt<D>(pts, 8 * Ib + rho);
-          const double u[4] = {sq_dist<D>(pa, pc0), sq_dist<D>(pa, pc1), sq_dist<D>(pb, pc0),
-                               sq_dist<D>(pb, pc1)};
-          double o[4];
-          cov_n<F, 4>(u, tab64, o);
-          c[Ia][0] = o[0];
-          c[Ia][1] = o[1];
-          c[Ib][0] = o[2];
-          c[Ib][1] = o[3];
-          if (Ia == J) fix_diag(Ia);
-        };
-        auto eval_one = [&](int Ia) {
-          const Pt<D> pa = ld_pt<D>(pts, 8 * Ia + rho);
-          const double u[2] = {sq_dist<D>(pa, pc0), sq_dist<D>(pa, pc1)};
-          double o[2];
-          cov_n<F, 2>(u, tab64, o);
-          c[Ia][0] = o[0];
-          c[Ia][1] = o[1];
-          if (Ia == J) fix_diag(Ia);
-        };
-        auto load_last = [&]() {
-          const double2 v = *reinterpret_cast<const double2*>(Ls + SL.s[T - 1][J] * 64 + 2 * lane);
-          const double2 yv = *reinterpret_cast<const double2*>(ys + j0);
-          const bool isy = rho == nel;
-          const double y0 = (isy && j0 < k) ? yv.x : 0.0, y1 = (isy && j1 < k) ? yv.y : 0.0;
-          c[T - 1][0] = (rho < nel) ? v.x : y0;
-          c[T - 1][1] = (rho < nel) ? v.y : y1;
-        };
-        auto eval_corner = [&]() {
-          const int i = W + rho;
-          const Pt<D> pr = ld_pt<D>(pts, min(i, k));
-          const double u[2] = {sq_dist<D>(pr, pc0), sq_dist<D>(pr, pc1)};
-          double o[2];
-          cov_n<F, 2>(u, tab64, o);
-          const double y0 = ys[min(j0, k)], y1 = ys[min(j1, k)];
-          const double dg = (i < k) ? onep : 1.0;
-          const bool krow = i <= k, yrow = i == k + 1;
-          double r0 = (krow && j0 < k) ? o[0] : ((yrow && j0 < k) ? y0 : 0.0);
-          double r1 = (krow && j1 < k) ? o[1] : ((yrow && j1 < k) ? y1 : 0.0);
-          r0 = (krow && i == j0) ? dg : r0;
-          r1 = (krow && i == j1) ? dg : r1;
-          c[T - 1][0] = r0;
-          c[T - 1][1] = r1;
-        };
-        auto frag = [&](int I, int P) -> double2 {
-          return (I == J) ? ljs[P]
-                          : *reinterpret_cast<const double2*>(Ls + SL.s[I][P] * 64 + 2 * lane);
-        };
-        auto update_two = [&](int Ia, int Ib) {
-#pragma unroll
-          for (int P = 0; P < J; ++P) {
-            const double2 la = frag(Ia, P), lb = frag(Ib, P);
-            dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
-            dmma_free(c[Ib][0], c[Ib][1], lb.x, b0[P]);
-            dmma_free(c[Ia][0], c[Ia][1], la.y, b1[P]);
-            dmma_free(c[Ib][0], c[Ib][1], lb.y, b1[P]);
-          }
-        };
-        auto update_one = [&](int Ia) {
-          if (J >= 2) {
-            double x0 = 0.0, x1 = 0.0;
-#pragma unroll
-            for (int P = 0; P < J; ++P) {
-              const double2 la = frag(Ia, P);
-              dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
-              dmma_free(x0, x1, la.y, b1[P]);
-            }
-            c[Ia][0] += x0;
-            c[Ia][1] += x1;
-          } else {
-#pragma unroll
-            for (int P = 0; P < J; ++P) {
-              const double2 la = frag(Ia, P);
-              dmma_free(c[Ia][0], c[Ia][1], la.x, b0[P]);
-              dmma_free(c[Ia][0], c[Ia][1], la.y, b1[P]);
-            }
-          }
-        };
-        auto work_item = [&](int m) {
-          const int Ia = J + 2 + 2 * m, Ib = Ia + 1;
-          if (J > T - 3 || Ia > T - 1) return;
-          if (Ib <= T - 2) {
-            eval_two(Ia, Ib);
-            update_two(Ia, Ib);
-          } else if (Ia <= T - 2) {
-            eval_one(Ia);
-            load_last();
-            update_two(Ia, T - 1);
-          } else {
-            load_last();
-            update_one(T - 1);
-          }
-        };
-
-        if (J <= T - 3) {
-          eval_two(J, J + 1);
-          update_two(J, J + 1);
-        } else if (J == T - 2) {
-          eval_one(J);
-          load_last();
-          update_two(J, T - 1);
-        } else {
-          eval_corner();
-          update_one(J);
-        }
-        // hand the updated diagonal tile to the factor warp ...
-        *reinterpret_cast<double2*>(Xin + 2 * lane) = make_double2(c[J][0], c[J][1]);
-        bar_arrive(1, TP_THREADS);
-        // ... and go on with the tiles below the diagonal, which do not depend on it
-#pragma unroll
-        for (int m = 0; m < 4; ++m) work_item(m);
-        bar_sync(2, TP_THREADS);  // M_J, 1/d and the outputs of this column are in place
-        ok = ok && (xo[3] != 0.0);
-        // xo[0..2]: entries (n,n), (n+1,n), (n+1,n+1) of the tile after its n = ncols steps
-        if (J == T - 1) {
-          if (kl < 7) {
-            out_var = xo[0];
-            out_mean = -xo[1];
-            out_yky = -xo[2];
-          } else {
-            out_yky = -xo[0];
-          }
-        }
-        if (J == T - 2 && kl == 7) out_var = xo[0];
-        if (J + 1 < T) {
-          const double2 bm = *reinterpret_cast<const double2*>(Xout + 2 * lane);
-          double n0[T], n1[T];
-#pragma unroll
-          for (int I = J + 1; I < T; ++I) {
-            n0[I] = 0.0;
-            n1[I] = 0.0;
-            dmma_free(n0[I], n1[I], c[I][0], bm.x);
-          }
-#pragma unroll
-          for (int I = J + 1; I < T; ++I) {
-            dmma_free(n0[I], n1[I], c[I][1], bm.y);
-            *reinterpret_cast<double2*>(Ls + SL.s[I][J] * 64 + 2 * lane) =
-                make_double2(n0[I], n1[I]);
-          }
-          if (J == T - 2 && kl == 7) out_mean = -shfl_d(n1[T - 1], 3);
-        }
+      build_column(0, 0, pts, ys);
+      if (it > 0) {
+        // the last column of the previous neighbourhood
+        bar_sync(2, TP_THREADS);
+        read_factor_outputs(T - 1);
+        write_outputs(prev_row, prev_q);
       }
-
-      if (lane == 0 && live) {
-        if (a.var) a.var[row] = ok ? a.scale * out_var : nan;
-        if (a.mean) a.mean[row] = ok ? out_mean : nan;
-        if (a.yky) a.yky[row] = ok ? out_yky : nan;
-        if (a.status) a.status[row] = ok ? 0 : 1;
-        if (loo.warp_rec) {
-          double* acc = s_acc[warp];
-          if (ok) {
-            const double err = out_mean - a.train_y[q_src];
-            const double e2 = err * err;
-            acc[MGP_P_SQERR] += e2;
-            acc[MGP_P_COUNT] += 1.0;
-            acc[MGP_P_YKY] += out_yky;
-            acc[MGP_P_ROWS] += 1.0;
-            acc[MGP_P_SQERR_V] += e2 / out_var;
-            acc[MGP_P_LOGV] += log(out_var);
-            if (loo.loss_id == MGP_LOSS_PSEUDO_HUBER) {
-              const double z = err / loo.boundary_scale;
-              acc[MGP_P_AUX] +=
-                  loo.boundary_scale * loo.boundary_scale * (sqrt(fma(z, z, 1.0)) - 1.0);
-            }
-          } else {
-            acc[MGP_P_BAD] += 1.0;
-          }
-        }
+      ok = true;
+      hand_off(0);
+#pragma unroll
+      for (int J = 0; J + 1 < T; ++J) {
+        build_column(J + 1, J, pts, ys);
+        bar_sync(2, TP_THREADS);
+        read_factor_outputs(J);
+        finish_column(J);
+        hand_off(J + 1);
       }
+      prev_row = row;
+      prev_q = q_src;
       q_src = q_next;
-      __syncwarp();
+    }
+    if (iters > 0) {
+      bar_sync(2, TP_THREADS);
+      read_factor_outputs(T - 1);
+      write_outputs(prev_row, prev_q);
     }
     cp_async_wait_all();
   }
