@@ -22,3 +22,9 @@ extern "C" int one_run(const double* x, const double* q, const int64_t* nn, cons
   ColLoo loo = {}; loo.peers.world = 1;
   return launch_tp_one<7, 1, 2>(a, loo, b, nullptr, (cudaStream_t)stream);
 }
+
+#ifdef MGP_TP_TRACE
+extern "C" int one_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, mgp::g_tp_trace, sizeof(long long) * 32 * 64);
+}
+#endif

@@ -69,6 +69,19 @@ constexpr TpSlots<T> tp_make_slots() {
   return m;
 }
 
+#ifdef MGP_TP_TRACE
+__device__ long long g_tp_trace[32][64];
+__device__ __forceinline__ long long tp_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+#define TP_TRACE(w, e) \
+  do { if (blockIdx.x == 3 && it == 20 && lane == 0) g_tp_trace[w][e] = tp_clock(); } while (0)
+#else
+#define TP_TRACE(w, e) do { } while (0)
+#endif
+
 __device__ __forceinline__ void bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -96,6 +109,21 @@ static inline size_t tp_warp_doubles(int k, int d) {
 //                   below it are preset once per kernel) -- the B-fragment order of the DMMAs
 //   xo[0..2]     = entries (n,n), (n+1,n), (n+1,n+1) of the partially eliminated tile, n = ncols
 //   xo[3]        = 1 if every pivot was positive, finite and normal
+// -1/p: MUFU.RCP64H seed (~20 bits, sign flipped on the integer pipe) + one third-order step;
+// bit-identical to -rcp_fast(p)
+__device__ __forceinline__ double neg_rcp_fast(double p) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+  const double nr = __hiloint2double(__double2hiint(r) ^ 0x80000000, __double2loint(r));
+  const double e = fma(-p, r, 1.0);
+  const double q1 = nr * e;
+  const double w = 1.0 + e;
+  return fma(q1, w, nr);
+}
+
+// FULL: all eight columns are eliminated (every tile column but the last two): no predicates, no
+// zero fill, nothing captured.
+template <bool FULL>
 __device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
                                                double* __restrict__ xout,
                                                double* __restrict__ dinv,
@@ -111,34 +139,36 @@ __device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
     }
   }
   double v[8][8];
+  if (!FULL) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v[r][c] = 0.0;
+      for (int c = 0; c < 8; ++c) v[r][c] = 0.0;
+  }
   double nd[8];
   double cap0 = 0.0, cap1 = 0.0, cap2 = 0.0;
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    nd[j] = -0.0;
-    if (j < ncols) {
+    if (!FULL) nd[j] = -0.0;
+    if (FULL || j < ncols) {
       const double p = a[j][j];
       ok = ok && ((unsigned)(__double2hiint(p) - 1) < 0x7fefffffu);
-      const double pinv = rcp_fast(p);
-      nd[j] = -pinv;
-      double l[8];
+      const double npinv = neg_rcp_fast(p);
+      nd[j] = npinv;
+      double nl[8];  // negated multipliers -a[c][j] / p
 #pragma unroll
-      for (int c = j + 1; c < 8; ++c) l[c] = a[c][j] * pinv;
+      for (int c = j + 1; c < 8; ++c) nl[c] = a[c][j] * npinv;
 #pragma unroll
       for (int c = j + 1; c < 8; ++c) {
 #pragma unroll
-        for (int i = c; i < 8; ++i) a[i][c] = fma(-a[i][j], l[c], a[i][c]);
+        for (int i = c; i < 8; ++i) a[i][c] = fma(a[i][j], nl[c], a[i][c]);
       }
 #pragma unroll
       for (int c = j + 1; c < 8; ++c) {
 #pragma unroll
-        for (int r = 0; r < j; ++r) v[r][c] = fma(-v[r][j], l[c], v[r][c]);
-        v[j][c] = -l[c];
+        for (int r = 0; r < j; ++r) v[r][c] = fma(v[r][j], nl[c], v[r][c]);
+        v[j][c] = nl[c];
       }
     } else if (j == ncols) {
       cap0 = a[j][j];
@@ -160,8 +190,12 @@ __device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
       *reinterpret_cast<double2*>(xout + 8 * c + r) = make_double2(lo, hi);
     }
   }
-  *reinterpret_cast<double2*>(xo) = make_double2(cap0, cap1);
-  *reinterpret_cast<double2*>(xo + 2) = make_double2(cap2, ok ? 1.0 : 0.0);
+  if (FULL) {
+    xo[3] = ok ? 1.0 : 0.0;
+  } else {
+    *reinterpret_cast<double2*>(xo) = make_double2(cap0, cap1);
+    *reinterpret_cast<double2*>(xo + 2) = make_double2(cap2, ok ? 1.0 : 0.0);
+  }
 }
 
 template <int T, int F, int D>
@@ -174,7 +208,13 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
   constexpr int NREC = MGP_PARTIALS;
   __shared__ double s_acc[TP_UWARPS][NREC];
   for (int e = threadIdx.x; e < TP_UWARPS * NREC; e += blockDim.x) (&s_acc[0][0])[e] = 0.0;
+  // MGP_TP_FACTOR_FIRST: the factor warp is warp 0 (the oldest warp of the CTA)
+#ifdef MGP_TP_FACTOR_FIRST
+  const int lane = threadIdx.x & 31, hw_warp = threadIdx.x >> 5;
+  const int warp = hw_warp == 0 ? TP_UWARPS : hw_warp - 1;
+#else
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#endif
   const int rho = lane >> 2, q = lane & 3, qb = lane & ~3;
   const int k = a.k;
   const int nel = k + 1 - W;
@@ -199,9 +239,16 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
       for (int J = 0; J < T; ++J) {
         const int ncols = (J <= T - 3) ? 8 : max(0, min(8, k - 8 * J));
         bar_sync(1, TP_THREADS);  // every update warp has parked its updated diagonal tile
-        if (lane < TP_UWARPS)
-          tp_factor_tile(base + OFF_XIN, base + OFF_XOUT, base + OFF_DINV + 8 * J, base + OFF_XO,
-                         ncols);
+        TP_TRACE(TP_UWARPS, 2 * J);
+        if (lane < TP_UWARPS) {
+          if (J <= T - 3)
+            tp_factor_tile<true>(base + OFF_XIN, base + OFF_XOUT, base + OFF_DINV + 8 * J,
+                                 base + OFF_XO, 8);
+          else
+            tp_factor_tile<false>(base + OFF_XIN, base + OFF_XOUT, base + OFF_DINV + 8 * J,
+                                  base + OFF_XO, ncols);
+        }
+        TP_TRACE(TP_UWARPS, 2 * J + 1);
         bar_arrive(2, TP_THREADS);
       }
     }
@@ -249,6 +296,7 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
     s0 = load_src(wglobal + wstride, lane);
     s1 = load_src(wglobal + wstride, lane + 32);
 
+    long long it = 0;
     // ---- results of one neighbourhood (called one pipeline stage after its last column) -----
     bool ok = true;
     double out_var = 0.0, out_mean = 0.0, out_yky = 0.0;
@@ -302,7 +350,8 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
     // Build tile column J: evaluate its entries and subtract the products with the finished tile
     // columns P < NP.  (NP = J - 1 in the pipeline: column J - 1 is still with the factor warp;
     // its term is added by finish_column.)
-    auto build_column = [&](int J, int NP, const double* pts, const double* ys) {
+    auto build_column = [&](int J, int NP, const double* pts, const double* ys, int Ilo = 0,
+                            int Ihi = T) {
       const int j0 = 8 * J + 2 * q, j1 = j0 + 1;
       const Pt<D> pc0 = ld_pt<D>(pts, (J == T - 1) ? min(j0, k) : j0);
       const Pt<D> pc1 = ld_pt<D>(pts, (J == T - 1) ? min(j1, k) : j1);
@@ -405,6 +454,7 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
 #pragma unroll
       for (int Ia = J; Ia < T; Ia += 2) {
         const int Ib = Ia + 1;
+        if (Ia < Ilo || Ia >= Ihi) continue;
         if (J == T - 1) {
           eval_corner();
           update_one(T - 1);
@@ -422,11 +472,13 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
       }
     };
 
-    // Column J has been built: hand its diagonal tile to the factor warp, park the tiles
-    // below it (raw) in the slots their finished versions will take.
+    // Column J has been built: hand its diagonal tile to the factor warp ...
     auto hand_off = [&](int J) {
       *reinterpret_cast<double2*>(Xin + 2 * lane) = make_double2(c[J][0], c[J][1]);
       bar_arrive(1, TP_THREADS);
+    };
+    // ... and park the tiles below it (raw) in the slots their finished versions will take.
+    auto park_below = [&](int J) {
 #pragma unroll
       for (int I = J + 1; I < T; ++I)
         *reinterpret_cast<double2*>(Ls + SL.s[I][J] * 64 + 2 * lane) =
@@ -434,7 +486,9 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
     };
 
     // M_J and 1/d_J are in place: finish the tiles below the diagonal (U = S M, two DMMAs per
-    // tile) and subtract column J's term from column J + 1, which sits in c[][].
+    // tile) and subtract column J's term from column J + 1, which sits in c[][].  The factor
+    // warp idles until it gets the next diagonal tile, so tile row J + 1 goes first and is
+    // handed off before the other rows are touched.
     auto finish_column = [&](int J) {
       if (J + 1 >= T) return;
       const double2 bm = *reinterpret_cast<const double2*>(Xout + 2 * lane);
@@ -444,23 +498,37 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
 #pragma unroll
       for (int I = J + 1; I < T; ++I)
         raw[I] = *reinterpret_cast<const double2*>(Ls + SL.s[I][J] * 64 + 2 * lane);
+      {
+        const int I = J + 1;
+        n0[I] = 0.0;
+        n1[I] = 0.0;
+        dmma_free(n0[I], n1[I], raw[I].x, bm.x);
+        dmma_free(n0[I], n1[I], raw[I].y, bm.y);
+      }
+      const double bj0 = n0[J + 1] * nd.x, bj1 = n1[J + 1] * nd.y;
+      dmma_free(c[J + 1][0], c[J + 1][1], n0[J + 1], bj0);
+      dmma_free(c[J + 1][0], c[J + 1][1], n1[J + 1], bj1);
+      hand_off(J + 1);
+      TP_TRACE(warp, 32 + J);
+      *reinterpret_cast<double2*>(Ls + SL.s[J + 1][J] * 64 + 2 * lane) =
+          make_double2(n0[J + 1], n1[J + 1]);
 #pragma unroll
-      for (int I = J + 1; I < T; ++I) {
+      for (int I = J + 2; I < T; ++I) {
         n0[I] = 0.0;
         n1[I] = 0.0;
         dmma_free(n0[I], n1[I], raw[I].x, bm.x);
       }
 #pragma unroll
-      for (int I = J + 1; I < T; ++I) {
+      for (int I = J + 2; I < T; ++I) {
         dmma_free(n0[I], n1[I], raw[I].y, bm.y);
         *reinterpret_cast<double2*>(Ls + SL.s[I][J] * 64 + 2 * lane) = make_double2(n0[I], n1[I]);
       }
       if (J == T - 2 && kl == 7) out_mean = -shfl_d(n1[T - 1], 3);
-      const double bj0 = n0[J + 1] * nd.x, bj1 = n1[J + 1] * nd.y;
 #pragma unroll
-      for (int I = J + 1; I < T; ++I) dmma_free(c[I][0], c[I][1], n0[I], bj0);
+      for (int I = J + 2; I < T; ++I) dmma_free(c[I][0], c[I][1], n0[I], bj0);
 #pragma unroll
-      for (int I = J + 1; I < T; ++I) dmma_free(c[I][0], c[I][1], n1[I], bj1);
+      for (int I = J + 2; I < T; ++I) dmma_free(c[I][0], c[I][1], n1[I], bj1);
+      park_below(J + 1);
     };
 
     // Software pipeline, one stage per tile column: while the factor warp works on the
@@ -468,8 +536,9 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
     // column 0 of the NEXT neighbourhood, staging and compact evaluation included.
     int buf = 0;
     long long prev_row = 0, prev_q = 0;
-    for (long long it = 0; it < iters; ++it, buf ^= 1) {
+    for (it = 0; it < iters; ++it, buf ^= 1) {
       const long long row = wglobal + it * wstride;
+      TP_TRACE(warp, 3);
       cp_async_wait_all();
       __syncwarp();
       const long long q_next = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);
@@ -493,6 +562,26 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
       }
       __syncwarp();
 
+      // Column 0 of this neighbourhood.  The factor warp is idle as soon as it has finished the
+      // last column of the previous neighbourhood, so the diagonal tile goes first and is handed
+      // off before anything else is evaluated (T >= 3: the first tile pair is regular).
+      constexpr int FIRST = (T >= 3) ? 2 : 0;
+      if (FIRST) build_column(0, 0, pts, ys, 0, FIRST);
+      TP_TRACE(warp, 1);
+      auto prev_done = [&]() {
+        if (it > 0) {
+          // the last column of the previous neighbourhood
+          bar_sync(2, TP_THREADS);
+          TP_TRACE(warp, 2);
+          read_factor_outputs(T - 1);
+          write_outputs(prev_row, prev_q);
+        }
+        ok = true;
+      };
+      if (FIRST) {
+        prev_done();
+        hand_off(0);
+      }
       // compact evaluation of the real rows of the last tile row (columns < W); the slots are
       // free: every finished tile of the previous neighbourhood was last read while its last
       // column was built
@@ -521,22 +610,22 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
         else if (base < total) chunk(base, std::integral_constant<int, 1>());
         __syncwarp();
       }
-      build_column(0, 0, pts, ys);
-      if (it > 0) {
-        // the last column of the previous neighbourhood
-        bar_sync(2, TP_THREADS);
-        read_factor_outputs(T - 1);
-        write_outputs(prev_row, prev_q);
+      TP_TRACE(warp, 0);
+      build_column(0, 0, pts, ys, FIRST, T);
+      if (!FIRST) {
+        prev_done();
+        hand_off(0);
       }
-      ok = true;
-      hand_off(0);
+      park_below(0);
 #pragma unroll
       for (int J = 0; J + 1 < T; ++J) {
         build_column(J + 1, J, pts, ys);
+        TP_TRACE(warp, 4 * J + 4);
         bar_sync(2, TP_THREADS);
+        TP_TRACE(warp, 4 * J + 5);
         read_factor_outputs(J);
         finish_column(J);
-        hand_off(J + 1);
+        TP_TRACE(warp, 4 * J + 6);
       }
       prev_row = row;
       prev_q = q_src;
