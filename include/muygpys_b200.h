@@ -142,8 +142,9 @@ int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_idx_host,
 
 /* Test/bench hook: 0 = choose automatically (column-direct > tile > generic), 1 = always the
  * generic shared-memory kernel, 2 = the register-tile DMMA kernel where supported, 3 = the
- * column-direct kernel (error if the shape is unsupported).  Lets the independently written
- * variants be cross-checked on identical inputs. */
+ * column-direct kernels (error if the shape is unsupported), 4 = the column-direct kernel with
+ * lane-parallel column steps even where the thread-per-tile kernel would be taken.  Lets the
+ * independently written variants be cross-checked on identical inputs. */
 int mgp_set_fused_variant(int32_t variant);
 
 /* One leave-one-out objective evaluation in ONE launch (a14-a16): the fused kernel over a

@@ -9,6 +9,10 @@ int launch_fused_col_f0(const mgp_problem*, const Model&, const ColLoo&, int*, c
 int launch_fused_col_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_col_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_col_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_tp_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_tp_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_tp_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_tp_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_colg_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_colg_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_colg_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
@@ -40,6 +44,14 @@ int fused_col_supported(const mgp_problem* p, const Model& model) {
   return 1;
 }
 
+static int tp_min_tiles() {
+  static const int v = [] {
+    const char* e = getenv("MGP_TP_MIN_T");  // dev switch
+    return e ? atoi(e) : 2;
+  }();
+  return v;
+}
+
 static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& loo, int* grid_out,
                       cudaStream_t stream) {
   if (loo.grad != nullptr || loo.backsub) {
@@ -51,6 +63,19 @@ static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& lo
       default:
         set_error("column kernel does not support this kernel / metric pair");
         return MGP_ERR_UNSUPPORTED;
+    }
+  }
+  // Plain prediction and the one-launch objective: the thread-per-tile kernel (fused_tp.cuh)
+  // from T = MGP_TP_MIN_T tile rows on -- below that a neighbourhood is so small that the
+  // factor warp's latency per tile column is not covered by the update warps' work.
+  // Variant 4 keeps the lane-parallel column kernel for cross-checks.
+  if (fused_variant() != 4 && col_tiles(p->k) >= tp_min_tiles()) {
+    switch (col_formula(model)) {
+      case F_M05: return launch_fused_tp_f0(p, model, loo, grid_out, stream);
+      case F_M15: return launch_fused_tp_f1(p, model, loo, grid_out, stream);
+      case F_M25: return launch_fused_tp_f2(p, model, loo, grid_out, stream);
+      case F_GAUSS: return launch_fused_tp_f3(p, model, loo, grid_out, stream);
+      default: break;
     }
   }
   switch (col_formula(model)) {

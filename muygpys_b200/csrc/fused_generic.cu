@@ -226,9 +226,9 @@ extern "C" int mgp_fused_posterior(const mgp_problem* p, void* ws, size_t ws_byt
   if (rc != MGP_OK) return rc;
   if (p->b == 0) return MGP_OK;
   const int variant = mgp::fused_variant();
-  if ((variant == 0 || variant == 3) && mgp::fused_col_supported(p, model))
+  if ((variant == 0 || variant == 3 || variant == 4) && mgp::fused_col_supported(p, model))
     return mgp::launch_fused_col(p, model, (cudaStream_t)stream);
-  if (variant == 3) {
+  if (variant == 3 || variant == 4) {
     mgp::set_error("the column-direct kernel does not support this shape");
     return MGP_ERR_UNSUPPORTED;
   }

@@ -32,7 +32,7 @@
 namespace mgp {
 
 static const int g_gram_off = getenv("MGP_NO_GRAM") != nullptr;  // dev switch: generic kernel for d > 8
-static int g_variant = 0;  // 0 auto (col > tile > generic), 1 generic, 2 tile, 3 col
+static int g_variant = 0;  // 0 auto (col > tile > generic), 1 generic, 2 tile, 3 col, 4 col (lane-parallel steps)
 
 int fused_variant() { return g_variant; }
 
@@ -80,8 +80,9 @@ int launch_fused_tile(const mgp_problem* p, const Model& model, void* ws, size_t
 }  // namespace mgp
 
 extern "C" int mgp_set_fused_variant(int32_t variant) {
-  if (variant < 0 || variant > 3) {
-    mgp::set_error("variant must be 0 (auto), 1 (generic), 2 (tile) or 3 (column-direct)");
+  if (variant < 0 || variant > 4) {
+    mgp::set_error("variant must be 0 (auto), 1 (generic), 2 (tile), 3 (column-direct) or 4 "
+                   "(column-direct with lane-parallel column steps)");
     return MGP_ERR_BAD_ARG;
   }
   mgp::g_variant = variant;

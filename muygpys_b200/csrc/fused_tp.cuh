@@ -29,14 +29,10 @@
 namespace mgp {
 namespace {
 
-#ifndef MGP_TP_UWARPS
-#define MGP_TP_UWARPS 8
-#endif
-#ifndef MGP_TP_MINB
-#define MGP_TP_MINB 2
-#endif
-constexpr int TP_UWARPS = MGP_TP_UWARPS;
-constexpr int TP_THREADS = (TP_UWARPS + 1) * 32;
+// Update warps per CTA (one CTA per SM).  16 warps is what 128 registers per thread allow: four
+// warps per scheduler (the register file is split per scheduler, so a 17th warp would cap
+// everybody at 96).  Shared memory limits T = 8 to fewer update warps (tp_update_warps).
+constexpr int TP_MAX_UWARPS = 15;
 
 // ---- shared-memory slots of the finished tiles, reused over the factorisation --------------
 // Tile (I,P), I > P, is written at the end of tile column P and last read during the update of
@@ -198,11 +194,12 @@ __device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
   }
 }
 
-template <int T, int F, int D>
-__global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
+template <int T, int F, int D, int TP_UWARPS>
+__global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     fused_tp_kernel(const TileArgs a, const ColLoo loo, int pts_doubles, int ys_doubles,
                     int warp_doubles, long long iters) {
   extern __shared__ double smem[];
+  constexpr int TP_THREADS = (TP_UWARPS + 1) * 32;
   constexpr TpSlots<T> SL = tp_make_slots<T>();
   constexpr int W = 8 * (T - 1);
   constexpr int NREC = MGP_PARTIALS;
@@ -683,43 +680,65 @@ __global__ void __launch_bounds__(TP_THREADS, MGP_TP_MINB)
   }
 }
 
-template <int T, int F, int D>
-int launch_tp_one(const TileArgs& a, const ColLoo& loo, long long rows, int* grid_out,
-                  cudaStream_t stream) {
+// ---- host side --------------------------------------------------------------------------
+template <int T, int F, int D, int U>
+int launch_tp_inst(const TileArgs& a, const ColLoo& loo, long long rows, int* grid_out,
+                   cudaStream_t stream) {
+  constexpr int THREADS = (U + 1) * 32;
   const int pts_doubles = (((a.k + 1) * D) + 1) & ~1;
   const int ys_doubles = (a.k + 2) & ~1;
   const size_t warp_doubles = tp_warp_doubles<T>(a.k, D);
-  const size_t smem = warp_doubles * TP_UWARPS * sizeof(double);
+  const size_t smem = warp_doubles * U * sizeof(double);
   cudaFuncAttributes fa;
-  MGP_REQUIRE(cudaFuncGetAttributes(&fa, fused_tp_kernel<T, F, D>) == cudaSuccess, MGP_ERR_CUDA,
-              "cudaFuncGetAttributes failed");
+  MGP_REQUIRE(cudaFuncGetAttributes(&fa, fused_tp_kernel<T, F, D, U>) == cudaSuccess,
+              MGP_ERR_CUDA, "cudaFuncGetAttributes failed");
   const size_t smem_cap = (size_t)max_smem_optin() - fa.sharedSizeBytes;
   MGP_REQUIRE(smem <= smem_cap, MGP_ERR_UNSUPPORTED,
-              "warp-specialised kernel shared memory %zu too large", smem);
+              "thread-per-tile kernel shared memory %zu too large", smem);
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(fused_tp_kernel<T, F, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(fused_tp_kernel<T, F, D, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem_cap);
     attr_set[dev] = true;
   }
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_tp_kernel<T, F, D>,
-                                                    TP_THREADS, smem) != cudaSuccess ||
-      per_sm < 1)
-    per_sm = 1;
-  long long blocks = (rows + TP_UWARPS - 1) / TP_UWARPS;
-  const long long cap = (long long)sm_count() * per_sm;
+  // one CTA per SM (launch bounds); every update warp of a CTA runs the same number of
+  // neighbourhoods, rows past the end of the batch repeat the last row and write nothing
+  long long blocks = (rows + U - 1) / U;
+  const long long cap = sm_count();
   if (blocks > cap) blocks = cap;
   if (grid_out) {
+    // a fixed grid keeps the partials' summation order independent of the batch size
     blocks = *grid_out > 0 ? *grid_out : cap;
     *grid_out = (int)blocks;
   }
-  const long long iters = (rows + blocks * TP_UWARPS - 1) / (blocks * TP_UWARPS);
-  fused_tp_kernel<T, F, D><<<(unsigned)blocks, TP_THREADS, smem, stream>>>(
+  const long long iters = (rows + blocks * U - 1) / (blocks * U);
+  fused_tp_kernel<T, F, D, U><<<(unsigned)blocks, THREADS, smem, stream>>>(
       a, loo, pts_doubles, ys_doubles, (int)warp_doubles, iters);
   return check_launch("fused_tp_kernel");
+}
+
+// update warps per CTA for this shape: as many as shared memory holds, at most TP_MAX_UWARPS
+template <int T>
+static inline int tp_update_warps(int k, int d) {
+  const size_t per_warp = tp_warp_doubles<T>(k, d) * sizeof(double);
+  const size_t avail = (size_t)max_smem_optin() - 4096;  // static shared memory + reserve
+  int u = (int)(avail / per_warp);
+  return u > TP_MAX_UWARPS ? TP_MAX_UWARPS : u;
+}
+
+template <int T, int F, int D>
+int launch_tp_one(const TileArgs& a, const ColLoo& loo, long long rows, int* grid_out,
+                  cudaStream_t stream) {
+  const int u = tp_update_warps<T>(a.k, D);
+  if (u >= TP_MAX_UWARPS)
+    return launch_tp_inst<T, F, D, TP_MAX_UWARPS>(a, loo, rows, grid_out, stream);
+  if constexpr (T == COL_MAX_T && D == 3) {  // k = 55..62 in three dimensions: 14 fit
+    if (u >= 13) return launch_tp_inst<T, F, D, 13>(a, loo, rows, grid_out, stream);
+  }
+  set_error("thread-per-tile kernel: T=%d d=%d k=%d does not fit in shared memory", T, D, a.k);
+  return MGP_ERR_UNSUPPORTED;
 }
 
 }  // namespace

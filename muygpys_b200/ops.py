@@ -116,7 +116,8 @@ def as_2d(x: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------
 def set_fused_variant(variant: int) -> None:
     """0 = auto, 1 = generic shared-memory kernel, 2 = register-tile DMMA kernel, 3 = the
-    column-direct kernel."""
+    column-direct kernels (thread-per-tile where built), 4 = the column-direct kernel with
+    lane-parallel column steps."""
     L.check(L.lib().mgp_set_fused_variant(int(variant)))
 
 

@@ -558,12 +558,16 @@ def test_kernels_follow_their_tensors_to_a_second_device():
         assert np.abs(mean).max() > 1e-3
 
 
+@pytest.mark.parametrize("col_variant", [3, 4])
 @pytest.mark.parametrize("d", [1, 2, 3])
-def test_column_kernel_shape_sweep(d):
-    """The column-direct kernel (variant 3, forced: an unsupported shape would raise) against
-    the numpy oracle for every neighbour count around its tile boundaries -- the augmented rows
-    (cross-covariance, targets) move through the last two tile rows as k changes -- and every
-    covariance function it builds, prediction and training-batch (query_idx) forms."""
+def test_column_kernel_shape_sweep(d, col_variant):
+    """The column-direct kernels (forced: an unsupported shape would raise) -- variant 3 = the
+    thread-per-tile kernel (factor warp + update warps, csrc/fused_tp.cuh), variant 4 = the
+    kernel with lane-parallel column steps (csrc/fused_col.cuh) -- against the numpy oracle for
+    every neighbour count around the tile boundaries -- the augmented rows (cross-covariance,
+    targets) move through the last two tile rows as k changes -- and every covariance function
+    they build, prediction and training-batch (query_idx) forms.  64 rows do not fill the last
+    CTA of the thread-per-tile kernel (15 neighbourhoods per CTA): the padding rows are covered."""
     from muygpys_b200 import ops
 
     rng = np.random.default_rng(40 + d)
@@ -581,7 +585,7 @@ def test_column_kernel_shape_sweep(d):
             ls = rng.uniform(0.2, 0.5, size=d) if (d > 1 and k % 2) else 0.3
             kw = dict(kernel_id=kid, metric_id=metric, length_scale=ls, noise=1e-3, scale=1.3,
                       want_yky=True, want_status=True)
-            ops.set_fused_variant(3)
+            ops.set_fused_variant(col_variant)
             got = ops.fused_posterior(dev(x), dev(q), None, dev(nn), dev(y), **kw)
             ops.set_fused_variant(1)
             ref = ops.fused_posterior(dev(x), dev(q), None, dev(nn), dev(y), **kw)
@@ -596,7 +600,7 @@ def test_column_kernel_shape_sweep(d):
         bi = np.sort(rng.choice(n, b, replace=False))
         bnn, _ = O.knn_exact(x, x[bi], k + 1)
         bnn = np.ascontiguousarray(bnn[:, 1:])
-        ops.set_fused_variant(3)
+        ops.set_fused_variant(col_variant)
         got = ops.fused_posterior(dev(x), dev(x), dev(bi), dev(bnn), dev(y), kernel_id=2,
                                   metric_id=0, length_scale=0.3, noise=1e-3)
         want_mean, want_var = O.predict(2, 0, 0.3, 1e-3, 1.0, x, y[:, 0], x, bi, bnn)
@@ -604,6 +608,7 @@ def test_column_kernel_shape_sweep(d):
         assert_close(got["var"].cpu().numpy(), want_var, RTOL, "batch var")
         # a non-positive pivot is reported, not hidden: negative nugget on duplicated points
         nn, _ = O.knn_exact(x, x[[3]], 10)
+        ops.set_fused_variant(col_variant)
         bad = ops.fused_posterior(dev(x), dev(x[[3]]), None, dev(nn), dev(y), kernel_id=2,
                                   metric_id=0, length_scale=0.3, noise=-1e-3, want_status=True)
         assert int(bad["status"][0]) == 1 and bool(torch.isnan(bad["mean"]).all())
