@@ -150,10 +150,11 @@ __device__ __forceinline__ void cov_n(const double (&u2)[N], double tab64, doubl
   }
   if (F == F_M15) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) out[i] = (1.0 + s[i]) * p[i];
+    for (int i = 0; i < N; ++i) out[i] = fma(s[i], p[i], p[i]);  // (1 + s) e^-s
   } else if (F == F_M25) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) out[i] = fma(u2[i], 1.0 / 3.0, 1.0 + s[i]) * p[i];
+    for (int i = 0; i < N; ++i)  // (1 + s + s^2 / 3) e^-s
+      out[i] = fma(fma(u2[i], 1.0 / 3.0, s[i]), p[i], p[i]);
   } else {
 #pragma unroll
     for (int i = 0; i < N; ++i) out[i] = p[i];

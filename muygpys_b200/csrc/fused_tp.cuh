@@ -32,7 +32,10 @@ namespace {
 // Update warps per CTA (one CTA per SM).  16 warps is what 128 registers per thread allow: four
 // warps per scheduler (the register file is split per scheduler, so a 17th warp would cap
 // everybody at 96).  Shared memory limits T = 8 to fewer update warps (tp_update_warps).
-constexpr int TP_MAX_UWARPS = 15;
+#ifndef MGP_TP_MAX_UWARPS
+#define MGP_TP_MAX_UWARPS 15
+#endif
+constexpr int TP_MAX_UWARPS = MGP_TP_MAX_UWARPS;
 
 // ---- shared-memory slots of the finished tiles, reused over the factorisation --------------
 // Tile (I,P), I > P, is written at the end of tile column P and last read during the update of
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
 
     // The tile column under construction: rows J .. T-1 as accumulator fragments.
     double c[T][2];
+    auto slot_off = [&](int I, int P) -> int { return SL.s[I][P] * 64; };
 
     // Build tile column J: evaluate its entries and subtract the products with the finished tile
     // columns P < NP.  (NP = J - 1 in the pipeline: column J - 1 is still with the factor warp;
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       double2 ljs[T];
 #pragma unroll
       for (int P = 0; P < NP; ++P) {
-        ljs[P] = *reinterpret_cast<const double2*>(Ls + SL.s[J][P] * 64 + 2 * lane);
+        ljs[P] = *reinterpret_cast<const double2*>(Ls + slot_off(J, P) + 2 * lane);
         const double2 nd = *reinterpret_cast<const double2*>(dinv_s + 8 * P + 2 * q);
         b0[P] = ljs[P].x * nd.x;
         b1[P] = ljs[P].y * nd.y;
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       };
       // last tile row left of its diagonal tile: parked values, target row, zero padding
       auto load_last = [&]() {
-        const double2 v = *reinterpret_cast<const double2*>(Ls + SL.s[T - 1][J] * 64 + 2 * lane);
+        const double2 v = *reinterpret_cast<const double2*>(Ls + slot_off(T - 1, J) + 2 * lane);
         const double2 yv = *reinterpret_cast<const double2*>(ys + j0);
         const bool isy = rho == nel;
         const double y0 = (isy && j0 < k) ? yv.x : 0.0, y1 = (isy && j1 < k) ? yv.y : 0.0;
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       };
       auto frag = [&](int I, int P) -> double2 {
         return (I == J) ? ljs[P]
-                        : *reinterpret_cast<const double2*>(Ls + SL.s[I][P] * 64 + 2 * lane);
+                        : *reinterpret_cast<const double2*>(Ls + slot_off(I, P) + 2 * lane);
       };
       auto update_two = [&](int Ia, int Ib) {
 #pragma unroll
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     auto park_below = [&](int J) {
 #pragma unroll
       for (int I = J + 1; I < T; ++I)
-        *reinterpret_cast<double2*>(Ls + SL.s[I][J] * 64 + 2 * lane) =
+        *reinterpret_cast<double2*>(Ls + slot_off(I, J) + 2 * lane) =
             make_double2(c[I][0], c[I][1]);
     };
 
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       double2 raw[T];
 #pragma unroll
       for (int I = J + 1; I < T; ++I)
-        raw[I] = *reinterpret_cast<const double2*>(Ls + SL.s[I][J] * 64 + 2 * lane);
+        raw[I] = *reinterpret_cast<const double2*>(Ls + slot_off(I, J) + 2 * lane);
       {
         const int I = J + 1;
         n0[I] = 0.0;
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       dmma_free(c[J + 1][0], c[J + 1][1], n1[J + 1], bj1);
       hand_off(J + 1);
       TP_TRACE(warp, 32 + J);
-      *reinterpret_cast<double2*>(Ls + SL.s[J + 1][J] * 64 + 2 * lane) =
+      *reinterpret_cast<double2*>(Ls + slot_off(J + 1, J) + 2 * lane) =
           make_double2(n0[J + 1], n1[J + 1]);
 #pragma unroll
       for (int I = J + 2; I < T; ++I) {
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
 #pragma unroll
       for (int I = J + 2; I < T; ++I) {
         dmma_free(n0[I], n1[I], raw[I].y, bm.y);
-        *reinterpret_cast<double2*>(Ls + SL.s[I][J] * 64 + 2 * lane) = make_double2(n0[I], n1[I]);
+        *reinterpret_cast<double2*>(Ls + slot_off(I, J) + 2 * lane) = make_double2(n0[I], n1[I]);
       }
       if (J == T - 2 && kl == 7) out_mean = -shfl_d(n1[T - 1], 3);
 #pragma unroll
@@ -528,24 +532,17 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       park_below(J + 1);
     };
 
-    // Software pipeline, one stage per tile column: while the factor warp works on the
-    // diagonal tile of column J, this warp builds column J + 1 -- for J = T - 1 that is
-    // column 0 of the NEXT neighbourhood, staging and compact evaluation included.
-    int buf = 0;
-    long long prev_row = 0, prev_q = 0;
-    for (it = 0; it < iters; ++it, buf ^= 1) {
-      const long long row = wglobal + it * wstride;
-      TP_TRACE(warp, 3);
+    // ---- preparation of a neighbourhood, in pieces that need nothing from the factor warp.
+    // For the NEXT neighbourhood (1) and (2) run where this warp would otherwise wait for the
+    // factor warp: the last two tile columns (the update work per column shrinks towards the
+    // end of the factorisation, the factor warp's latency does not).  (A second slot set for
+    // the last tile row, so that (3) can move there too, was measured: no gain.)
+    // (1) its staging is complete: fold the length scales (and the Matern sqrt(2 nu)) into the
+    //     staged coordinates
+    auto prep_scale = [&](int nbuf) {
       cp_async_wait_all();
       __syncwarp();
-      const long long q_next = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);
-      issue_rows(buf ^ 1, lane, s0);
-      issue_rows(buf ^ 1, lane + 32, s1);
-      cp_async_commit();
-      s0 = load_src(row + 2 * wstride, lane);
-      s1 = load_src(row + 2 * wstride, lane + 32);
-      double* pts = pts_buf + buf * pts_doubles;
-      const double* ys = ys_buf + buf * ys_doubles;
+      double* pts = pts_buf + nbuf * pts_doubles;
       if (D == 2) {
         double2* p2 = reinterpret_cast<double2*>(pts);
         for (int i = lane; i <= k; i += 32) {
@@ -558,31 +555,27 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
         for (int e = lane; e < (k + 1) * D; e += 32) pts[e] *= a.coord_scale[e % D];
       }
       __syncwarp();
-
-      // Column 0 of this neighbourhood.  The factor warp is idle as soon as it has finished the
-      // last column of the previous neighbourhood, so the diagonal tile goes first and is handed
-      // off before anything else is evaluated (T >= 3: the first tile pair is regular).
-      constexpr int FIRST = (T >= 3) ? 2 : 0;
-      if (FIRST) build_column(0, 0, pts, ys, 0, FIRST);
-      TP_TRACE(warp, 1);
-      auto prev_done = [&]() {
-        if (it > 0) {
-          // the last column of the previous neighbourhood
-          bar_sync(2, TP_THREADS);
-          TP_TRACE(warp, 2);
-          read_factor_outputs(T - 1);
-          write_outputs(prev_row, prev_q);
-        }
-        ok = true;
-      };
-      if (FIRST) {
-        prev_done();
-        hand_off(0);
-      }
-      // compact evaluation of the real rows of the last tile row (columns < W); the slots are
-      // free: every finished tile of the previous neighbourhood was last read while its last
-      // column was built
+    };
+    // (2) the other staging buffer is free (no evaluation of the current neighbourhood is left):
+    //     start the staging of the neighbourhood after `nx`; first tile pair of column 0
+    long long q_next = 0;
+    constexpr int FIRST = (T >= 3) ? 2 : 0;  // T >= 3: the first tile pair of column 0 is regular
+    auto prep_stage_and_first = [&](long long nx, int nbuf) {
+      const long long row = wglobal + nx * wstride;
+      q_next = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);  // query of row nx + 1
+      issue_rows(nbuf ^ 1, lane, s0);
+      issue_rows(nbuf ^ 1, lane + 32, s1);
+      cp_async_commit();
+      s0 = load_src(row + 2 * wstride, lane);
+      s1 = load_src(row + 2 * wstride, lane + 32);
+      if (FIRST)
+        build_column(0, 0, pts_buf + nbuf * pts_doubles, ys_buf + nbuf * ys_doubles, 0, FIRST);
+    };
+    // (3) compact evaluation of the real rows of the last tile row (columns < W) into the slots
+    //     of that row; they are free once the last column of the previous neighbourhood is built
+    auto prep_compact = [&](int nbuf) {
       if (T > 1) {
+        const double* pts = pts_buf + nbuf * pts_doubles;
         const int total = nel * W;
         auto chunk = [&](int base, auto nway) {
           constexpr int N = decltype(nway)::value;
@@ -607,16 +600,48 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
         else if (base < total) chunk(base, std::integral_constant<int, 1>());
         __syncwarp();
       }
-      TP_TRACE(warp, 0);
-      build_column(0, 0, pts, ys, FIRST, T);
-      if (!FIRST) {
-        prev_done();
-        hand_off(0);
+    };
+
+    // Software pipeline, one stage per tile column: while the factor warp works on the
+    // diagonal tile of column J, this warp builds column J + 1.
+    int buf = 0;
+    long long prev_row = 0, prev_q = 0;
+    if (iters > 0) {
+      prep_scale(0);
+      prep_stage_and_first(0, 0);
+    }
+    constexpr int J_SCALE = (T >= 3) ? T - 3 : 0;  // stage that hosts piece (1) of the next one
+    for (it = 0; it < iters; ++it, buf ^= 1) {
+      const long long row = wglobal + it * wstride;
+      const bool more = it + 1 < iters;
+      TP_TRACE(warp, 3);
+      const double* pts = pts_buf + buf * pts_doubles;
+      const double* ys = ys_buf + buf * ys_doubles;
+      const long long q_after = q_next;  // query of row it + 1
+      if (it > 0) {
+        // the last column of the previous neighbourhood
+        bar_sync(2, TP_THREADS);
+        TP_TRACE(warp, 2);
+        read_factor_outputs(T - 1);
+        write_outputs(prev_row, prev_q);
       }
+      ok = true;
+      if (!FIRST) {
+        prep_compact(buf);
+        build_column(0, 0, pts, ys, 0, T);
+      }
+      hand_off(0);
+      TP_TRACE(warp, 1);
+      if (FIRST) prep_compact(buf);
+      if (FIRST) build_column(0, 0, pts, ys, FIRST, T);
+      TP_TRACE(warp, 0);
       park_below(0);
 #pragma unroll
       for (int J = 0; J + 1 < T; ++J) {
         build_column(J + 1, J, pts, ys);
+        if (J == J_SCALE && more) prep_scale(buf ^ 1);
+        // column T - 1 is built: c[0 .. T-2] and this neighbourhood's staging buffer are free
+        if (J == T - 2 && more) prep_stage_and_first(it + 1, buf ^ 1);
         TP_TRACE(warp, 4 * J + 4);
         bar_sync(2, TP_THREADS);
         TP_TRACE(warp, 4 * J + 5);
@@ -626,7 +651,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       }
       prev_row = row;
       prev_q = q_src;
-      q_src = q_next;
+      q_src = q_after;
     }
     if (iters > 0) {
       bar_sync(2, TP_THREADS);
