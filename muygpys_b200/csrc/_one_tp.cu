@@ -9,7 +9,7 @@ int sm_count() { return 148; }
 int max_smem_optin() { return 227 * 1024; }
 }
 extern "C" const char* one_err() { return mgp::g_err2; }
-extern "C" int one_slots() { return mgp::tp_make_slots<7>().count; }
+
 extern "C" int one_run(const double* x, const double* q, const int64_t* nn, const double* y, long long n,
                        long long b, int k, double ls, double noise, double* mean, double* var, void* stream) {
   using namespace mgp;
@@ -20,7 +20,10 @@ extern "C" int one_run(const double* x, const double* q, const int64_t* nn, cons
   Model m = {}; m.kernel_id = p.kernel_id; m.metric_id = 0; m.d = 2; m.inv_ls = 1.0 / ls;
   TileArgs a; fill_tile_args(&p, m, a);
   ColLoo loo = {}; loo.peers.world = 1;
-  return launch_tp_one<7, 1, 2>(a, loo, b, nullptr, (cudaStream_t)stream);
+#ifndef ONE_T
+#define ONE_T 7
+#endif
+  return launch_tp_one<ONE_T, 1, 2>(a, loo, b, nullptr, (cudaStream_t)stream);
 }
 
 #ifdef MGP_TP_TRACE

@@ -2,13 +2,14 @@
 // formula: fused_col_m05.cu, _m15.cu, _m25.cu, _gauss.cu) and the one-launch leave-one-out
 // objective entry point mgp_fused_loo.
 #include "fused_col.cuh"
+#include "fused_tp.cuh"
 
 namespace mgp {
 
-int launch_fused_col_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
-int launch_fused_col_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
-int launch_fused_col_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
-int launch_fused_col_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_tp_big_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_tp_big_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_tp_big_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+int launch_fused_tp_big_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_tp_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_tp_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_tp_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
@@ -34,27 +35,34 @@ static int col_formula(const Model& model) {
   return model.kernel_id == MGP_KERNEL_RBF ? F_GAUSS : -1;
 }
 
-int fused_col_supported(const mgp_problem* p, const Model& model) {
+// Shapes the column-direct kernels take: r = 1, d <= 3, homoscedastic nugget, the four closed
+// covariance formulas; k = 7..102 (T = 2..13 tile rows) for plain prediction and the one-launch
+// objective (thread-per-tile kernel), k <= 62 (T <= 8) where the back substitution is needed
+// (fast-mean coefficients, analytic gradient: GRAD instantiations of fused_col_kernel).
+static int col_shape_ok(const mgp_problem* p, const Model& model, int max_tiles) {
   if (p->r != 1 || p->d > 3 || p->noise_bk || !p->train_y) return 0;
   const int T = col_tiles(p->k);
-  if (T < 2 || T > COL_MAX_T) return 0;
+  if (T < 2 || T > max_tiles) return 0;
   if (col_formula(model) < 0) return 0;
   // 2-D points are fetched with one 16-byte cp.async each
   if (p->d == 2 && ((((uintptr_t)p->train_x) | ((uintptr_t)p->query_x)) & 15)) return 0;
   return 1;
 }
 
-static int tp_min_tiles() {
-  static const int v = [] {
-    const char* e = getenv("MGP_TP_MIN_T");  // dev switch
-    return e ? atoi(e) : 2;
-  }();
-  return v;
+int fused_col_supported(const mgp_problem* p, const Model& model) {
+  return col_shape_ok(p, model, p->coeffs ? COL_MAX_T : TP_MAX_T);
 }
 
 static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& loo, int* grid_out,
                       cudaStream_t stream) {
-  if (loo.grad != nullptr || loo.backsub) {
+  const int T = col_tiles(p->k);
+  // Back substitution wanted, or variant 4 (cross-check of the thread-per-tile kernel with the
+  // lane-parallel column kernel: its GRAD instantiation, whose back substitution then goes
+  // unused): fused_col_kernel<T, F, D, true>.
+  if (loo.grad != nullptr || loo.backsub || (fused_variant() == 4 && T <= COL_MAX_T)) {
+    MGP_REQUIRE(T <= COL_MAX_T, MGP_ERR_UNSUPPORTED,
+                "coefficients / analytic gradient: k = %d needs more than %d tile rows", p->k,
+                COL_MAX_T);
     switch (col_formula(model)) {
       case F_M05: return launch_fused_colg_f0(p, model, loo, grid_out, stream);
       case F_M15: return launch_fused_colg_f1(p, model, loo, grid_out, stream);
@@ -66,27 +74,40 @@ static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& lo
     }
   }
   // Plain prediction and the one-launch objective: the thread-per-tile kernel (fused_tp.cuh)
-  // from T = MGP_TP_MIN_T tile rows on -- below that a neighbourhood is so small that the
-  // factor warp's latency per tile column is not covered by the update warps' work.
-  // Variant 4 keeps the lane-parallel column kernel for cross-checks.
-  if (fused_variant() != 4 && col_tiles(p->k) >= tp_min_tiles()) {
-    switch (col_formula(model)) {
-      case F_M05: return launch_fused_tp_f0(p, model, loo, grid_out, stream);
-      case F_M15: return launch_fused_tp_f1(p, model, loo, grid_out, stream);
-      case F_M25: return launch_fused_tp_f2(p, model, loo, grid_out, stream);
-      case F_GAUSS: return launch_fused_tp_f3(p, model, loo, grid_out, stream);
-      default: break;
-    }
-  }
+  const bool big = T > COL_MAX_T;
   switch (col_formula(model)) {
-    case F_M05: return launch_fused_col_f0(p, model, loo, grid_out, stream);
-    case F_M15: return launch_fused_col_f1(p, model, loo, grid_out, stream);
-    case F_M25: return launch_fused_col_f2(p, model, loo, grid_out, stream);
-    case F_GAUSS: return launch_fused_col_f3(p, model, loo, grid_out, stream);
+    case F_M05:
+      return (big ? launch_fused_tp_big_f0 : launch_fused_tp_f0)(p, model, loo, grid_out, stream);
+    case F_M15:
+      return (big ? launch_fused_tp_big_f1 : launch_fused_tp_f1)(p, model, loo, grid_out, stream);
+    case F_M25:
+      return (big ? launch_fused_tp_big_f2 : launch_fused_tp_f2)(p, model, loo, grid_out, stream);
+    case F_GAUSS:
+      return (big ? launch_fused_tp_big_f3 : launch_fused_tp_f3)(p, model, loo, grid_out, stream);
     default:
       set_error("column kernel does not support this kernel / metric pair");
       return MGP_ERR_UNSUPPORTED;
   }
+}
+
+// Neighbourhoods in flight per SM for the kernel a problem takes (the host-buffer pipeline cuts
+// its chunks on multiples of one wave): update warps of the thread-per-tile kernel, 12 for the
+// tile kernels.
+int fused_wave_per_sm(const mgp_problem* p) {
+  Model model;
+  if (make_model(p->kernel_id, p->metric_id, p->d, p->length_scale_count, p->length_scale,
+                 &model) != MGP_OK ||
+      !fused_col_supported(p, model) || p->coeffs)
+    return 12;
+  const int T = col_tiles(p->k), D = p->d;
+#define MGP_U_CASE(TT) \
+  case TT: return D == 1 ? tp_uwarps<TT, 1>() : D == 2 ? tp_uwarps<TT, 2>() : tp_uwarps<TT, 3>();
+  switch (T) {
+    MGP_U_CASE(2) MGP_U_CASE(3) MGP_U_CASE(4) MGP_U_CASE(5) MGP_U_CASE(6) MGP_U_CASE(7)
+    MGP_U_CASE(8) MGP_U_CASE(9) MGP_U_CASE(10) MGP_U_CASE(11) MGP_U_CASE(12) MGP_U_CASE(13)
+    default: return 12;
+  }
+#undef MGP_U_CASE
 }
 
 int launch_fused_col(const mgp_problem* p, const Model& model, cudaStream_t stream) {
@@ -172,9 +193,9 @@ extern "C" int mgp_fused_loo_grad(const mgp_problem* p, int32_t loss_id, double 
   rc = make_model(p->kernel_id, p->metric_id, p->d, p->length_scale_count, p->length_scale,
                   &model);
   if (rc != MGP_OK) return rc;
-  MGP_REQUIRE(fused_col_supported(p, model), MGP_ERR_UNSUPPORTED,
-              "mgp_fused_loo: shape not supported by the column kernel (k=%d d=%d r=%d)", p->k,
-              p->d, p->r);
+  MGP_REQUIRE(col_shape_ok(p, model, grad ? COL_MAX_T : TP_MAX_T), MGP_ERR_UNSUPPORTED,
+              "mgp_fused_loo: shape not supported by the column kernels (k=%d d=%d r=%d%s)", p->k,
+              p->d, p->r, grad ? ", analytic gradient" : "");
   MGP_REQUIRE(p->query_x == p->train_x && p->query_idx != nullptr, MGP_ERR_BAD_ARG,
               "mgp_fused_loo expects a training batch: query_x == train_x and batch indices in "
               "query_idx");

@@ -800,7 +800,8 @@ __global__ void __launch_bounds__(COL_WARPS * 32, GRAD ? 3 : MGP_COL_MINB)
         if (threadIdx.x < MGP_PARTIALS) {
           s_tot[threadIdx.x] = tot;
           if (loo.peers.world <= 1) loo.partials[threadIdx.x] = tot;
-        } else if (GRAD && threadIdx.x < MGP_PARTIALS + MGP_GRAD_DOUBLES) {
+        } else if (GRAD && loo.grad != nullptr &&
+                   threadIdx.x < MGP_PARTIALS + MGP_GRAD_DOUBLES) {
           loo.grad[threadIdx.x - MGP_PARTIALS] = tot;
         }
       }

@@ -288,13 +288,28 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       if (i < k) cp_async8(ys_buf + buf * ys_doubles + i, a.train_y + src);
     };
 
-    long long s0 = load_src(wglobal, lane), s1 = load_src(wglobal, lane + 32);
-    long long q_src = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);
-    issue_rows(0, lane, s0);
-    issue_rows(0, lane + 32, s1);
+    // lane l stages points l, l + 32, ... (point k is the query); k + 1 <= 8 T - 1
+    constexpr int NS = (8 * T - 1 + 31) / 32;
+    long long sidx[NS];
+    auto load_all = [&](long long row) {
+#pragma unroll
+      for (int m = 0; m < NS; ++m) sidx[m] = load_src(row, lane + 32 * m);
+    };
+    auto issue_all = [&](int buf) {
+#pragma unroll
+      for (int m = 0; m < NS; ++m) issue_rows(buf, lane + 32 * m, sidx[m]);
+    };
+    auto query_of_staged = [&]() -> long long {
+      long long v = sidx[0];
+#pragma unroll
+      for (int m = 1; m < NS; ++m) v = ((k >> 5) == m) ? sidx[m] : v;
+      return __shfl_sync(0xffffffffu, v, k & 31);
+    };
+    load_all(wglobal);
+    long long q_src = query_of_staged();
+    issue_all(0);
     cp_async_commit();
-    s0 = load_src(wglobal + wstride, lane);
-    s1 = load_src(wglobal + wstride, lane + 32);
+    load_all(wglobal + wstride);
 
     long long it = 0;
     // ---- results of one neighbourhood (called one pipeline stage after its last column) -----
@@ -562,12 +577,10 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     constexpr int FIRST = (T >= 3) ? 2 : 0;  // T >= 3: the first tile pair of column 0 is regular
     auto prep_stage_and_first = [&](long long nx, int nbuf) {
       const long long row = wglobal + nx * wstride;
-      q_next = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);  // query of row nx + 1
-      issue_rows(nbuf ^ 1, lane, s0);
-      issue_rows(nbuf ^ 1, lane + 32, s1);
+      q_next = query_of_staged();  // query of row nx + 1
+      issue_all(nbuf ^ 1);
       cp_async_commit();
-      s0 = load_src(row + 2 * wstride, lane);
-      s1 = load_src(row + 2 * wstride, lane + 32);
+      load_all(row + 2 * wstride);
       if (FIRST)
         build_column(0, 0, pts_buf + nbuf * pts_doubles, ys_buf + nbuf * ys_doubles, 0, FIRST);
     };
@@ -744,26 +757,25 @@ int launch_tp_inst(const TileArgs& a, const ColLoo& loo, long long rows, int* gr
   return check_launch("fused_tp_kernel");
 }
 
-// update warps per CTA for this shape: as many as shared memory holds, at most TP_MAX_UWARPS
-template <int T>
-static inline int tp_update_warps(int k, int d) {
-  const size_t per_warp = tp_warp_doubles<T>(k, d) * sizeof(double);
-  const size_t avail = (size_t)max_smem_optin() - 4096;  // static shared memory + reserve
-  int u = (int)(avail / per_warp);
+// Update warps per CTA: as many as shared memory holds for the largest k of this T (8 T - 2), at
+// most TP_MAX_UWARPS; T = 9 is capped at 11 so that the CTA has 12 warps -- three per scheduler,
+// 168 registers per thread (its tile column and B fragments do not fit in 128).
+constexpr int TP_MAX_T = 13;
+template <int T, int D>
+constexpr int tp_uwarps() {
+  constexpr int k = 8 * T - 2;
+  constexpr size_t pts = (size_t)((((k + 1) * D) + 1) & ~1), ys = (size_t)((k + 2) & ~1);
+  size_t n = (size_t)tp_make_slots<T>().count * 64 + 8 * (size_t)T + 64 + 64 + 8 + 2 * pts + 2 * ys;
+  while ((n & 15) != 2) n += 2;
+  int u = (int)((227 * 1024 - 4096) / (n * sizeof(double)));
+  if (T == 9 && u > 11) u = 11;
   return u > TP_MAX_UWARPS ? TP_MAX_UWARPS : u;
 }
 
 template <int T, int F, int D>
 int launch_tp_one(const TileArgs& a, const ColLoo& loo, long long rows, int* grid_out,
                   cudaStream_t stream) {
-  const int u = tp_update_warps<T>(a.k, D);
-  if (u >= TP_MAX_UWARPS)
-    return launch_tp_inst<T, F, D, TP_MAX_UWARPS>(a, loo, rows, grid_out, stream);
-  if constexpr (T == COL_MAX_T && D == 3) {  // k = 55..62 in three dimensions: 14 fit
-    if (u >= 13) return launch_tp_inst<T, F, D, 13>(a, loo, rows, grid_out, stream);
-  }
-  set_error("thread-per-tile kernel: T=%d d=%d k=%d does not fit in shared memory", T, D, a.k);
-  return MGP_ERR_UNSUPPORTED;
+  return launch_tp_inst<T, F, D, tp_uwarps<T, D>()>(a, loo, rows, grid_out, stream);
 }
 
 }  // namespace

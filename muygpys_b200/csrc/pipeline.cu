@@ -72,6 +72,7 @@ std::vector<long long> chunk_bounds(long long b, long long wave) {
 }  // namespace
 
 int validate_problem(const mgp_problem* p);
+int fused_wave_per_sm(const mgp_problem* p);
 
 }  // namespace mgp
 
@@ -122,7 +123,8 @@ extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_
   for (int i = 0; i < 2; ++i) MGP_CUDA(cudaStreamWaitEvent(ss->s[i], ss->fork, 0));
   forked = true;
 
-  const long long wave = 12LL * sm_count();
+  // one wave of the kernel this shape takes: neighbourhoods in flight per SM x SMs
+  const long long wave = (long long)fused_wave_per_sm(p) * sm_count();
   const std::vector<long long> bounds = chunk_bounds(p->b, wave);
   const long long k = p->k, r = p->r;
   for (size_t c = 0; c + 1 < bounds.size(); ++c) {

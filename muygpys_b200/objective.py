@@ -213,7 +213,8 @@ def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_in
     r = 1 if y.dim() == 1 else y.shape[1]
     if loss_fn.loss_id not in (L.LOSS_MSE, L.LOSS_LOOL):
         raise NotImplementedError(f"analytic gradient: loss {loss_fn.name} (mse and lool only)")
-    if not ops.fused_loo_supported(d, k, r, spec.kernel_id, spec.metric_id, spec.heteroscedastic):
+    if not ops.fused_loo_supported(d, k, r, spec.kernel_id, spec.metric_id, spec.heteroscedastic,
+                                   grad=True):
         raise NotImplementedError("analytic gradient: shape not supported by mgp_fused_loo_grad")
     lool = loss_fn.loss_id == L.LOSS_LOOL
     analytic = lool and spec.analytic

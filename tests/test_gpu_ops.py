@@ -577,6 +577,8 @@ def test_column_kernel_shape_sweep(d, col_variant):
     q = rng.uniform(size=(b, d))
     x[7] = x[3]  # an exact duplicate: zero distance inside neighbourhoods
     ks = [7, 8, 9, 14, 15, 16, 22, 23, 30, 31, 38, 39, 46, 47, 50, 54, 55, 62]
+    if col_variant == 3:  # the thread-per-tile kernel goes on to 13 tile rows (k = 102)
+        ks += [63, 64, 70, 71, 78, 79, 86, 87, 94, 95, 100, 102]
     try:
         for k in ks:
             nn, _ = O.knn_exact(x, q, k)
@@ -616,7 +618,8 @@ def test_column_kernel_shape_sweep(d, col_variant):
         ops.set_fused_variant(0)
 
 
-@pytest.mark.parametrize("loss_id,k,d", [(1, 50, 2), (2, 50, 2), (4, 30, 1), (2, 23, 3), (0, 62, 2)])
+@pytest.mark.parametrize("loss_id,k,d", [(1, 50, 2), (2, 50, 2), (4, 30, 1), (2, 23, 3), (0, 62, 2),
+                                         (2, 100, 2), (1, 71, 3)])
 def test_fused_loo_record_matches_two_pass_path(loss_id, k, d):
     """mgp_fused_loo (K1 with the loss / scale partials in its epilogue, one launch) against
     K1 + mgp_loss_partials on the same batch, slot by slot; repeated launches reuse the

@@ -6,7 +6,7 @@ import numpy as np, torch
 from muygpys_b200 import ops
 from muygpys_b200.neighbors import NN_Wrapper
 rng = np.random.default_rng(7)
-n, b, k = 1_000_000, 100_000, 50
+n, b, k = 1_000_000, int(os.environ.get('B', 100_000)), int(os.environ.get('K', 50))
 x = torch.as_tensor(rng.uniform(size=(n, 2))).cuda(); y = torch.as_tensor(rng.normal(size=n)).cuda()
 q = torch.as_tensor(rng.uniform(size=(b, 2))).cuda()
 nn, _ = NN_Wrapper(x, k).get_nns(q)
@@ -14,6 +14,14 @@ ops.set_fused_variant(2)
 ref = ops.fused_posterior(x, q, None, nn, y, kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 res = {}
+if os.environ.get("TIME_REF"):
+    ts = []
+    for _ in range(6):
+        flush.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.fused_posterior(x, q, None, nn, y, kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3); e.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(e))
+    print("library tile kernel (variant 2):", round(min(ts[1:]), 4), "ms", flush=True)
 only = os.environ.get("ONLY")  # comma-separated variant names
 for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "muygpys_b200", "csrc", "build", "libone_*.so"))):
     if only and os.path.basename(path)[7:-3] not in only.split(","):
