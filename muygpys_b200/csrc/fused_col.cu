@@ -10,10 +10,18 @@ int launch_fused_tp_big_f0(const mgp_problem*, const Model&, const ColLoo&, int*
 int launch_fused_tp_big_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_tp_big_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_tp_big_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
-int launch_fused_tp_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
-int launch_fused_tp_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
-int launch_fused_tp_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
-int launch_fused_tp_f3(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+// thread-per-tile kernel: one launcher per (formula, tile count), fused_tp_unit.cu
+#define MGP_TP_DECL(F, T)                                                                  \
+  int launch_fused_tp_f##F##_t##T(const mgp_problem*, const Model&, const ColLoo&, int*, \
+                                  cudaStream_t);
+#define MGP_TP_ALL_T(X, F)                                                                   \
+  X(F, 2) X(F, 3) X(F, 4) X(F, 5) X(F, 6) X(F, 7) X(F, 8) X(F, 9) X(F, 10) X(F, 11) X(F, 12) \
+      X(F, 13)
+MGP_TP_ALL_T(MGP_TP_DECL, 0)
+MGP_TP_ALL_T(MGP_TP_DECL, 1)
+MGP_TP_ALL_T(MGP_TP_DECL, 2)
+MGP_TP_ALL_T(MGP_TP_DECL, 3)
+#undef MGP_TP_DECL
 int launch_fused_colg_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_colg_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_colg_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
@@ -74,20 +82,17 @@ static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& lo
     }
   }
   // Plain prediction and the one-launch objective: the thread-per-tile kernel (fused_tp.cuh)
-  const bool big = T > COL_MAX_T;
-  switch (col_formula(model)) {
-    case F_M05:
-      return (big ? launch_fused_tp_big_f0 : launch_fused_tp_f0)(p, model, loo, grid_out, stream);
-    case F_M15:
-      return (big ? launch_fused_tp_big_f1 : launch_fused_tp_f1)(p, model, loo, grid_out, stream);
-    case F_M25:
-      return (big ? launch_fused_tp_big_f2 : launch_fused_tp_f2)(p, model, loo, grid_out, stream);
-    case F_GAUSS:
-      return (big ? launch_fused_tp_big_f3 : launch_fused_tp_f3)(p, model, loo, grid_out, stream);
-    default:
-      set_error("column kernel does not support this kernel / metric pair");
-      return MGP_ERR_UNSUPPORTED;
-  }
+  typedef int (*launcher)(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+#define MGP_TP_ENTRY(F, TT) launch_fused_tp_f##F##_t##TT,
+  static const launcher table[4][TP_MAX_T - 1] = {{MGP_TP_ALL_T(MGP_TP_ENTRY, 0)},
+                                                  {MGP_TP_ALL_T(MGP_TP_ENTRY, 1)},
+                                                  {MGP_TP_ALL_T(MGP_TP_ENTRY, 2)},
+                                                  {MGP_TP_ALL_T(MGP_TP_ENTRY, 3)}};
+#undef MGP_TP_ENTRY
+  const int f = col_formula(model);
+  MGP_REQUIRE(f >= 0 && f < 4 && T >= 2 && T <= TP_MAX_T, MGP_ERR_UNSUPPORTED,
+              "column kernels do not support this kernel / metric pair or k = %d", p->k);
+  return table[f][T - 2](p, model, loo, grid_out, stream);
 }
 
 // Neighbourhoods in flight per SM for the kernel a problem takes (the host-buffer pipeline cuts

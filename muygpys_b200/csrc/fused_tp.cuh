@@ -215,7 +215,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
 #else
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #endif
-  const int rho = lane >> 2, q = lane & 3, qb = lane & ~3;
+  const int rho = lane >> 2, q = lane & 3;
   const int k = a.k;
   const int nel = k + 1 - W;
   const int kl = k & 7;
@@ -577,6 +577,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     constexpr int FIRST = (T >= 3) ? 2 : 0;  // T >= 3: the first tile pair of column 0 is regular
     auto prep_stage_and_first = [&](long long nx, int nbuf) {
       const long long row = wglobal + nx * wstride;
+      __syncwarp();  // every lane has read what it needed from the buffer about to be refilled
       q_next = query_of_staged();  // query of row nx + 1
       issue_all(nbuf ^ 1);
       cp_async_commit();

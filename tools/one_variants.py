@@ -22,6 +22,22 @@ if os.environ.get("TIME_REF"):
         a.record(); ops.fused_posterior(x, q, None, nn, y, kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3); e.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(e))
     print("library tile kernel (variant 2):", round(min(ts[1:]), 4), "ms", flush=True)
+    ops.set_fused_variant(0)
+    ts = []
+    for _ in range(8):
+        flush.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.fused_posterior(x, q, None, nn, y, kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3); e.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(e))
+    print("library, automatic choice (variant 0):", round(min(ts[1:]), 4), "min", round(float(np.mean(ts[1:])), 4), "mean ms", flush=True)
+    ts = []
+    for _ in range(8):  # three flushes: the GPU is still busy when the launch is enqueued
+        flush.zero_(); flush.zero_(); flush.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.fused_posterior(x, q, None, nn, y, kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3); e.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(e))
+    print("library, launch enqueued under a longer flush:", round(min(ts[1:]), 4), "min", round(float(np.mean(ts[1:])), 4), "mean ms", flush=True)
+    ops.set_fused_variant(2)
 only = os.environ.get("ONLY")  # comma-separated variant names
 for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "muygpys_b200", "csrc", "build", "libone_*.so"))):
     if only and os.path.basename(path)[7:-3] not in only.split(","):

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small launches of every kernel family for compute-sanitizer (memcheck / racecheck /
-synccheck): column-direct (plain, LOO epilogue, gradient), tile (register and shared-memory
+synccheck): thread-per-tile (plain, LOO epilogue; T <= 8 and T = 13), column-direct with
+lane-parallel steps (coefficients, gradient, variant 4), tile (register and shared-memory
 factor, Gram d > 8), generic, host pipeline, KNN (grid, small-d, tiled, Gram pre-filter), fast
 mean, losses, staged ops, label mask."""
 import os, sys
@@ -17,17 +18,17 @@ for d, k, r in ((2, 50, 1), (1, 30, 1), (3, 23, 1), (2, 100, 1), (2, 50, 3), (20
     y = rng.normal(size=(n, r))
     xd, qd, yd = dev(x), dev(q), dev(y)
     nn, _ = ops.knn(xd, qd, k)
-    for variant in (0, 2, 1):
+    for variant in (0, 4, 2, 1) if (r == 1 and k <= 62 and d <= 3) else (0, 2, 1):
         ops.set_fused_variant(variant)
         ops.fused_posterior(xd, qd, None, nn, yd, kernel_id=2, metric_id=0, length_scale=0.3,
                             noise=1e-3, want_yky=True, want_status=True,
-                            want_coeffs=(variant != 0))
+                            want_coeffs=(variant not in (0, 4)))
     ops.set_fused_variant(0)
-    if r == 1 and k <= 62 and d <= 3:
+    if r == 1 and k <= 102 and d <= 3:
         bi = dev(np.sort(rng.choice(n, b, replace=False)))
         bnn, _ = ops.knn(xd, xd[bi], k + 1)
         bnn = bnn[:, 1:].contiguous()
-        for want_grad in (False, True):
+        for want_grad in ((False, True) if k <= 62 else (False,)):
             loo = ops.FusedLoo(xd, yd[:, 0].contiguous(), bi, bnn, kernel_id=2, metric_id=0,
                                loss_id=L.LOSS_LOOL, want_grad=want_grad)
             for _ in range(2):
