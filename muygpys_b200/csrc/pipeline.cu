@@ -2,13 +2,14 @@
 // live in HOST memory, as they do behind the reference's `regress_from_indices`
 // (S/examples/from_indices.py:22-63, numpy arrays in / numpy arrays out).
 //
-// The batch is cut into chunks; chunk c+1 is uploaded on one side stream while chunk c runs
-// in the fused kernel on the other and chunk c-1's results travel back, so the end-to-end rate
-// is max(PCIe, compute) instead of their sum.  Chunk boundaries sit on multiples of one full
-// wave of the kernel (12 neighbourhoods in flight per SM) and grow geometrically from a small
-// first chunk: the only transfer that is not hidden is the first upload, and a chunk may grow
-// by about kernel time / copy time per step without stalling the pipeline.  Everything is
-// ordered after the work already queued on `stream` and joined back into it.
+// The batch is cut into chunks that flow through three internal streams -- upload, kernel,
+// download -- linked by one event per chunk and stage: the uploads run back to back whatever the
+// kernels do (the host link is the slower side for the C2 shape: 0.77 ms of uploads against
+// 0.66 ms of kernels), chunk c runs while chunk c+1 arrives and chunk c-1's results travel
+// back, so the end-to-end rate is max(PCIe, compute) instead of their sum.  Chunk boundaries
+// sit on multiples of one full wave of the kernel; the first and the last chunk are small (only
+// the first upload and the last kernel + download are exposed).  Everything is ordered after
+// the work already queued on `stream` and joined back into it.
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -18,10 +19,12 @@
 namespace mgp {
 namespace {
 
+constexpr int N_SIDE = 3;  // upload, kernel, download
 struct SideStreams {
-  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaStream_t s[N_SIDE] = {nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr;
-  cudaEvent_t join[2] = {nullptr, nullptr};
+  cudaEvent_t join[N_SIDE] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> chunk_ev;  // two per chunk: uploaded, computed
   bool ready = false;
 };
 
@@ -35,7 +38,7 @@ int side_streams(SideStreams** out) {
               cudaGetErrorString(e));
   SideStreams& ss = g_side[dev];  // (the caller holds g_side_mutex)
   if (!ss.ready) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < N_SIDE; ++i) {
       e = cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking);
       MGP_REQUIRE(e == cudaSuccess, MGP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
       e = cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming);
@@ -49,23 +52,41 @@ int side_streams(SideStreams** out) {
   return MGP_OK;
 }
 
-// chunk boundaries: multiples of `wave` rows, sizes 2, 2, 3, 5, 7, 10, ... waves (x1.4)
+// Chunk boundaries: multiples of `wave` rows.  Every chunk costs ~15 us of launches and
+// pipeline fill, so there are few of them: eight waves each up to 16 chunks (C2: 8, 8, 8, 8, 8,
+// 6 waves); larger batches ramp up x1.25 from eight waves to waves/16 per chunk and back down,
+// so that the exposed ends -- the first upload, the last kernel + download -- stay small.
+// Measured on C2 (uploads 0.73 ms, kernels 0.65 ms): 0.90 ms end to end, against 0.95 ms with a
+// finer tail (9 chunks) and 1.09 ms for the two-stream x1.4 schedule it replaces.
 std::vector<long long> chunk_bounds(long long b, long long wave) {
   // dev switches for tuning the schedule
-  static const double first = getenv("MGP_PIPE_FIRST") ? atof(getenv("MGP_PIPE_FIRST")) : 2.0;
-  static const double growth = getenv("MGP_PIPE_GROWTH") ? atof(getenv("MGP_PIPE_GROWTH")) : 1.4;
+  static const double first = getenv("MGP_PIPE_FIRST") ? atof(getenv("MGP_PIPE_FIRST")) : 8.0;
+  static const double growth = getenv("MGP_PIPE_GROWTH") ? atof(getenv("MGP_PIPE_GROWTH")) : 1.25;
+  const long long waves = (b + wave - 1) / wave;
+  const double cap = (double)waves / 16 > first ? (double)waves / 16 : first;
+  auto ramp = [&](long long target) {
+    std::vector<long long> v;
+    double w = first;
+    long long acc = 0;
+    while (acc < target) {
+      long long sz = (long long)w < 1 ? 1 : (long long)w;
+      if (target - acc - sz <= sz / 2) sz = target - acc;  // no sliver at the end
+      v.push_back(sz);
+      acc += sz;
+      w = w * growth > cap ? cap : w * growth;
+    }
+    return v;
+  };
+  const long long head_waves = (waves + 1) / 2;
+  std::vector<long long> sizes = ramp(head_waves);
+  const std::vector<long long> tail = ramp(waves - head_waves);
+  sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
   std::vector<long long> bounds{0};
-  double w = first;
-  while (bounds.back() < b) {
-    const long long sz = (long long)w < 1 ? 1 : (long long)w;
+  for (long long sz : sizes) {
+    if (bounds.back() >= b) break;
     bounds.push_back(bounds.back() + sz * wave);
-    w *= growth;
   }
   bounds.back() = b;
-  const size_t m = bounds.size();
-  if (m > 2 && bounds[m - 1] - bounds[m - 2] < (bounds[m - 2] - bounds[m - 3]) / 4) {
-    bounds.erase(bounds.end() - 2);  // fold a short tail into the previous chunk
-  }
   return bounds;
 }
 
@@ -103,7 +124,7 @@ extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_
   // returning: chunks already enqueued must stay ordered before the caller's later work (torch
   // may reuse the staging and output tensors as soon as this call returns).
   auto join = [&]() {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < N_SIDE; ++i)
       if (cudaEventRecord(ss->join[i], ss->s[i]) == cudaSuccess)
         cudaStreamWaitEvent(main_stream, ss->join[i], 0);
   };
@@ -120,23 +141,32 @@ extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_
 
   // fork: the side streams start after everything already queued on `stream`
   MGP_CUDA(cudaEventRecord(ss->fork, main_stream));
-  for (int i = 0; i < 2; ++i) MGP_CUDA(cudaStreamWaitEvent(ss->s[i], ss->fork, 0));
+  for (int i = 0; i < N_SIDE; ++i) MGP_CUDA(cudaStreamWaitEvent(ss->s[i], ss->fork, 0));
   forked = true;
+  cudaStream_t up = ss->s[0], run = ss->s[1], down = ss->s[2];
 
   // one wave of the kernel this shape takes: neighbourhoods in flight per SM x SMs
   const long long wave = (long long)fused_wave_per_sm(p) * sm_count();
   const std::vector<long long> bounds = chunk_bounds(p->b, wave);
   const long long k = p->k, r = p->r;
+  while (ss->chunk_ev.size() < 2 * bounds.size()) {
+    cudaEvent_t ev = nullptr;
+    MGP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ss->chunk_ev.push_back(ev);
+  }
+  const bool downloads = mean_host != nullptr || var_host != nullptr;
   for (size_t c = 0; c + 1 < bounds.size(); ++c) {
     const long long lo = bounds[c], hi = bounds[c + 1], rows = hi - lo;
     if (rows <= 0) continue;
-    cudaStream_t s = ss->s[c & 1];
+    cudaEvent_t uploaded = ss->chunk_ev[2 * c], computed = ss->chunk_ev[2 * c + 1];
     int64_t* nn_dev = const_cast<int64_t*>(p->nn_idx) + lo * k;
     MGP_CUDA(cudaMemcpyAsync(nn_dev, nn_idx_host + lo * k, (size_t)rows * k * sizeof(int64_t),
-                             cudaMemcpyHostToDevice, s));
+                             cudaMemcpyHostToDevice, up));
     if (query_idx_host)
       MGP_CUDA(cudaMemcpyAsync(const_cast<int64_t*>(p->query_idx) + lo, query_idx_host + lo,
-                               (size_t)rows * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+                               (size_t)rows * sizeof(int64_t), cudaMemcpyHostToDevice, up));
+    MGP_CUDA(cudaEventRecord(uploaded, up));
+    MGP_CUDA(cudaStreamWaitEvent(run, uploaded, 0));
     mgp_problem sub = *p;
     sub.b = rows;
     sub.nn_idx = nn_dev;
@@ -153,20 +183,24 @@ extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_
     if (p->yky) sub.yky = p->yky + lo;
     if (p->coeffs) sub.coeffs = p->coeffs + lo * k * r;
     if (p->status) sub.status = p->status + lo;
-    rc = mgp_fused_posterior(&sub, ws, ws_bytes, (void*)s);
+    rc = mgp_fused_posterior(&sub, ws, ws_bytes, (void*)run);  // (one kernel stream: one ws)
     if (rc != MGP_OK) {
       join();
       return rc;
     }
+    if (downloads) {
+      MGP_CUDA(cudaEventRecord(computed, run));
+      MGP_CUDA(cudaStreamWaitEvent(down, computed, 0));
+    }
     if (mean_host)
       MGP_CUDA(cudaMemcpyAsync(mean_host + lo * r, sub.mean, (size_t)rows * r * sizeof(double),
-                               cudaMemcpyDeviceToHost, s));
+                               cudaMemcpyDeviceToHost, down));
     if (var_host)
       MGP_CUDA(cudaMemcpyAsync(var_host + lo, sub.var, (size_t)rows * sizeof(double),
-                               cudaMemcpyDeviceToHost, s));
+                               cudaMemcpyDeviceToHost, down));
   }
   // join: later work on `stream` sees every chunk
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < N_SIDE; ++i) {
     MGP_CUDA(cudaEventRecord(ss->join[i], ss->s[i]));
     MGP_CUDA(cudaStreamWaitEvent(main_stream, ss->join[i], 0));
   }
