@@ -236,7 +236,9 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     // M = L^-T run in that lane's registers (no shuffles, no selects)
     double* base = warp_base(lane < TP_UWARPS ? lane : 0);
     for (long long it = 0; it < iters; ++it) {
-      for (int J = 0; J < T; ++J) {
+      // (the last tile column -- at most six columns to eliminate, nothing below it -- stays
+      // with the update warps: see last_column)
+      for (int J = 0; J + 1 < T; ++J) {
         const int ncols = (J <= T - 3) ? 8 : max(0, min(8, k - 8 * J));
         bar_sync(1, TP_THREADS);  // every update warp has parked its updated diagonal tile
         TP_TRACE(TP_UWARPS, 2 * J);
@@ -346,16 +348,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     // pick up what the factor warp left for tile column J (after bar_sync(2))
     auto read_factor_outputs = [&](int J) {
       ok = ok && (xo[3] != 0.0);
-      // xo[0..2]: entries (n,n), (n+1,n), (n+1,n+1) of the tile after its n = ncols steps
-      if (J == T - 1) {
-        if (kl < 7) {
-          out_var = xo[0];
-          out_mean = -xo[1];
-          out_yky = -xo[2];
-        } else {
-          out_yky = -xo[0];
-        }
-      }
+      // xo[0]: entry (n,n) of the tile after its n = ncols steps
       if (J == T - 2 && kl == 7) out_var = xo[0];
     };
 
@@ -501,6 +494,43 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
             make_double2(c[I][0], c[I][1]);
     };
 
+    // The LAST tile column: its diagonal tile holds the last k - 8 (T - 1) <= 6 columns of K, the
+    // cross-covariance row and the target row, and nothing lies below it.  A round trip through
+    // the factor warp (hand-off, ~1 100 cycles of latency, pick-up) would leave this warp idle,
+    // so the few column steps run here, lane-parallel as in fused_col_kernel, and the outputs
+    // come straight out of the Schur complement.
+    auto last_column = [&]() {
+      constexpr int J = T - 1;
+      const int ncols = max(0, min(8, k - 8 * J));
+      const int qb = lane & ~3;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if (j < ncols) {
+          const int qj = j >> 1, bj = j & 1;
+          const double cj = bj == 0 ? c[J][0] : c[J][1];
+          const double p = shfl_d(cj, j * 4 + qj);
+          const double uc0 = shfl_d(cj, (2 * q) * 4 + qj);      // U[2q][j]
+          const double uc1 = shfl_d(cj, (2 * q + 1) * 4 + qj);  // U[2q+1][j]
+          const double lr = shfl_d(cj, qb | qj);                // U[row][j]
+          ok = ok && ((unsigned)(__double2hiint(p) - 1) < 0x7fefffffu);
+          const double pinv = rcp_fast(p);
+          const double t0 = sel_d(2 * q > j, uc0, 0.0) * pinv;
+          const double t1 = sel_d(2 * q + 1 > j, uc1, 0.0) * pinv;
+          c[J][0] = fma(-lr, t0, c[J][0]);
+          c[J][1] = fma(-lr, t1, c[J][1]);
+        }
+      }
+      if (kl < 7) {
+        const double cv = (kl & 1) ? c[J][1] : c[J][0];
+        const double cy = ((kl + 1) & 1) ? c[J][1] : c[J][0];
+        out_var = shfl_d(cv, kl * 4 + (kl >> 1));
+        out_mean = -shfl_d(cv, (kl + 1) * 4 + (kl >> 1));
+        out_yky = -shfl_d(cy, (kl + 1) * 4 + ((kl + 1) >> 1));
+      } else {
+        out_yky = -shfl_d(c[J][0], 0);
+      }
+    };
+
     // M_J and 1/d_J are in place: finish the tiles below the diagonal (U = S M, two DMMAs per
     // tile) and subtract column J's term from column J + 1, which sits in c[][].  The factor
     // warp idles until it gets the next diagonal tile, so tile row J + 1 goes first and is
@@ -524,7 +554,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       const double bj0 = n0[J + 1] * nd.x, bj1 = n1[J + 1] * nd.y;
       dmma_free(c[J + 1][0], c[J + 1][1], n0[J + 1], bj0);
       dmma_free(c[J + 1][0], c[J + 1][1], n1[J + 1], bj1);
-      hand_off(J + 1);
+      if (J + 1 < T - 1) hand_off(J + 1);
       TP_TRACE(warp, 32 + J);
       *reinterpret_cast<double2*>(Ls + slot_off(J + 1, J) + 2 * lane) =
           make_double2(n0[J + 1], n1[J + 1]);
@@ -589,29 +619,32 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     //     of that row; they are free once the last column of the previous neighbourhood is built
     auto prep_compact = [&](int nbuf) {
       if (T > 1) {
+        // lane l evaluates columns l, l + 32, ... of three rows at a time: six entries in
+        // flight, no index arithmetic, the column points loaded once (a flat 32-entries-per-pass
+        // list took 2 200 cycles for 144 entries: three dependent passes, a division per entry)
         const double* pts = pts_buf + nbuf * pts_doubles;
-        const int total = nel * W;
-        auto chunk = [&](int base, auto nway) {
-          constexpr int N = decltype(nway)::value;
-          double u[N], o[N];
-          int dst[N];
+        constexpr int NG = (W + 31) / 32;
+        for (int ar0 = 0; ar0 < nel; ar0 += 3) {
+          const Pt<D> pr0 = ld_pt<D>(pts, min(W + ar0, k)), pr1 = ld_pt<D>(pts, min(W + ar0 + 1, k)),
+                      pr2 = ld_pt<D>(pts, min(W + ar0 + 2, k));
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            const int e = base + 32 * i + lane;
-            const int ee = e < total ? e : 0;
-            const int ar = ee / W, j = ee - ar * W;
-            u[i] = sq_dist<D>(ld_pt<D>(pts, W + ar), ld_pt<D>(pts, j));
-            dst[i] = e < total ? (j >> 3) * 64 + ar * 8 + (j & 7) : -1;  // slot of (T-1, j/8)
+          for (int g = 0; g < NG; g += 2) {
+            const int j0 = 32 * g + lane, j1 = j0 + 32;
+            const bool v0 = j0 < W, v1 = (g + 1 < NG) && j1 < W;
+            const Pt<D> pc0 = ld_pt<D>(pts, v0 ? j0 : 0), pc1 = ld_pt<D>(pts, v1 ? j1 : 0);
+            const double u[6] = {sq_dist<D>(pr0, pc0), sq_dist<D>(pr1, pc0), sq_dist<D>(pr2, pc0),
+                                 sq_dist<D>(pr0, pc1), sq_dist<D>(pr1, pc1), sq_dist<D>(pr2, pc1)};
+            double o[6];
+            cov_n<F, 6>(u, tab64, o);
+            double* d0 = Ls + (j0 >> 3) * 64 + (j0 & 7);  // slot of (T-1, j/8) is j/8
+            double* d1 = Ls + (j1 >> 3) * 64 + (j1 & 7);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              if (v0 && ar0 + i < nel) d0[(ar0 + i) * 8] = o[i];
+              if (v1 && ar0 + i < nel) d1[(ar0 + i) * 8] = o[3 + i];
+            }
           }
-          cov_n<F, N>(u, tab64, o);
-#pragma unroll
-          for (int i = 0; i < N; ++i)
-            if (dst[i] >= 0) Ls[dst[i]] = o[i];
-        };
-        int base = 0;
-        for (; base + 64 < total; base += 96) chunk(base, std::integral_constant<int, 3>());
-        if (base + 32 < total) chunk(base, std::integral_constant<int, 2>());
-        else if (base < total) chunk(base, std::integral_constant<int, 1>());
+        }
         __syncwarp();
       }
     };
@@ -619,7 +652,6 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     // Software pipeline, one stage per tile column: while the factor warp works on the
     // diagonal tile of column J, this warp builds column J + 1.
     int buf = 0;
-    long long prev_row = 0, prev_q = 0;
     if (iters > 0) {
       prep_scale(0);
       prep_stage_and_first(0, 0);
@@ -632,13 +664,6 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       const double* pts = pts_buf + buf * pts_doubles;
       const double* ys = ys_buf + buf * ys_doubles;
       const long long q_after = q_next;  // query of row it + 1
-      if (it > 0) {
-        // the last column of the previous neighbourhood
-        bar_sync(2, TP_THREADS);
-        TP_TRACE(warp, 2);
-        read_factor_outputs(T - 1);
-        write_outputs(prev_row, prev_q);
-      }
       ok = true;
       if (!FIRST) {
         prep_compact(buf);
@@ -663,14 +688,10 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
         finish_column(J);
         TP_TRACE(warp, 4 * J + 6);
       }
-      prev_row = row;
-      prev_q = q_src;
+      if (T == 1) c[0][0] = c[0][1] = 0.0;  // (not instantiated)
+      last_column();
+      write_outputs(row, q_src);
       q_src = q_after;
-    }
-    if (iters > 0) {
-      bar_sync(2, TP_THREADS);
-      read_factor_outputs(T - 1);
-      write_outputs(prev_row, prev_q);
     }
     cp_async_wait_all();
   }
