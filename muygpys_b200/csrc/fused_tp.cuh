@@ -1,27 +1,36 @@
-// K1 (thread-per-tile variant of the column-direct kernel).
+// K1 (thread-per-tile variant of the column-direct kernel) -- the kernel bench.py times.
 //
 // fused_col_kernel spends 39 % of its instructions in the 52 in-tile LDL^T column steps of a
 // neighbourhood: lane-parallel steps (five 64-bit shuffles, a reciprocal, selects, six FP64
-// instructions: ~35 instructions per step) that use ~10 % of their FP64 lanes.  Here a CTA holds
-// TP_UWARPS update warps (one neighbourhood each) and ONE factor warp:
+// instructions: ~35 instructions per step) that use ~10 % of their FP64 lanes.  Here a CTA (one
+// per SM) holds U update warps (one neighbourhood each) and ONE factor warp:
 //
-//   * update warp: gather, evaluate the covariance entries of tile column J into accumulator
-//     fragments, DMMA-update them with the finished tile columns, park the updated DIAGONAL tile
-//     in 512 bytes of shared memory, go on with the tiles below the diagonal (which do not depend
-//     on the factorisation), then pick up M_J = L_JJ^-T (B-fragment order) and -1/d and finish
-//     the column with two DMMAs per tile;
+//   * update warp: gather, evaluate the covariance entries of a tile column straight into
+//     accumulator fragments, DMMA-update them with the finished tile columns, park the updated
+//     DIAGONAL tile in 512 bytes of shared memory (hand-off), later pick up M_J = L_JJ^-T
+//     (B-fragment order) and -1/d and finish the tiles below the diagonal with two DMMAs each;
 //   * factor warp: lane g factorises the diagonal tile of update warp g ENTIRELY IN ITS OWN
 //     REGISTERS -- 8x8 LDL^T (84 FMAs, 28 multiplies, 8 reciprocals) and M = L^-T (56 FMAs) on
-//     compile-time register indices, no shuffles, no selects: ~250 instructions for
-//     TP_UWARPS tiles instead of 8 x 35 per tile.  Same operations in the same order as the
-//     lane-parallel steps of fused_col_kernel: results are bit-identical.
+//     compile-time register indices, no shuffles, no selects: ~280 instructions for U tiles
+//     instead of 8 x 35 per tile.  Same operations in the same order as the lane-parallel steps
+//     of fused_col_kernel: results are bit-identical.
 //
-// Hand-offs use two named barriers (bar.arrive / bar.sync over the whole CTA).  Finished tiles
-// live in a shared-memory store whose slots are REUSED once a tile row is complete (15 instead
-// of 21 slots at T = 7).
+// Hand-offs use two named barriers over the CTA (1: tiles parked, 2: factors ready; bar.arrive
+// by the producer, bar.sync by the consumer).  The update warps run a software pipeline over
+// the tile columns: while the factor warp holds the diagonal tile of column J they build column
+// J + 1 without column J's term; when M_J arrives they finish tile (J+1, J) first, complete the
+// next diagonal tile and hand it off before touching the other rows.  The last tile column
+// (at most six columns to eliminate, nothing below it) is factorised by the update warp itself,
+// and the next neighbourhood is prepared (coordinate scaling, staging of the one after it,
+// first tile pair of column 0) in the last two stages, where the update warps would otherwise
+// wait for the factor warp.  Finished tiles live in a shared-memory store whose slots are
+// REUSED once a tile row is complete (15 instead of 21 slots at T = 7, 48 instead of 78 at
+// T = 13).
 //
-// Same numerics, layout and restrictions as fused_col_kernel (r == 1, d <= 3, 7 <= k <= 62,
-// homoscedastic nugget, no coefficient output, no gradient).
+// Same numerics and layout as fused_col_kernel; r == 1, d <= 3, homoscedastic nugget, 7 <= k <=
+// 102 (T = 2..13 tile rows); prediction and the one-launch objective (no coefficient output, no
+// gradient: those need the whole factor at the end and stay with fused_col_kernel).
+// DESIGN.md section 4 has the measurements and the variants that were tried and dropped.
 #pragma once
 
 #include "fused_col.cuh"
@@ -31,7 +40,7 @@ namespace {
 
 // Update warps per CTA (one CTA per SM).  16 warps is what 128 registers per thread allow: four
 // warps per scheduler (the register file is split per scheduler, so a 17th warp would cap
-// everybody at 96).  Shared memory limits T = 8 to fewer update warps (tp_update_warps).
+// everybody at 96).  Shared memory allows fewer from T = 8 on (tp_uwarps).
 #ifndef MGP_TP_MAX_UWARPS
 #define MGP_TP_MAX_UWARPS 15
 #endif
@@ -101,13 +110,6 @@ static inline size_t tp_warp_doubles(int k, int d) {
   return n;
 }
 
-// One lane: LDL^T of the first `ncols` columns of an 8x8 symmetric tile (row-major at xin,
-// lower triangle significant) and M = L^-T, the product of the column operations.
-//   dinv[c]      = -1/d_c (eliminated columns), -0 otherwise
-//   xout[8 c + r] = M[r][c] for r < c  (M is unit upper triangular; the diagonal and the zeros
-//                   below it are preset once per kernel) -- the B-fragment order of the DMMAs
-//   xo[0..2]     = entries (n,n), (n+1,n), (n+1,n+1) of the partially eliminated tile, n = ncols
-//   xo[3]        = 1 if every pivot was positive, finite and normal
 // -1/p: MUFU.RCP64H seed (~20 bits, sign flipped on the integer pipe) + one third-order step;
 // bit-identical to -rcp_fast(p)
 __device__ __forceinline__ double neg_rcp_fast(double p) {
@@ -120,8 +122,15 @@ __device__ __forceinline__ double neg_rcp_fast(double p) {
   return fma(q1, w, nr);
 }
 
+// One lane: LDL^T of the first `ncols` columns of an 8x8 symmetric tile (row-major at xin,
+// lower triangle significant) and M = L^-T, the product of the column operations.
+//   dinv[c]      = -1/d_c (eliminated columns), -0 otherwise
+//   xout[8 c + r] = M[r][c] for r < c  (M is unit upper triangular; the diagonal and the zeros
+//                   below it are preset once per kernel) -- the B-fragment order of the DMMAs
+//   xo[0..2]     = entries (n,n), (n+1,n), (n+1,n+1) of the partially eliminated tile, n = ncols
+//   xo[3]        = 1 if every pivot was positive, finite and normal
 // FULL: all eight columns are eliminated (every tile column but the last two): no predicates, no
-// zero fill, nothing captured.
+// zero fill, nothing captured (xo[3] only).
 template <bool FULL>
 __device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
                                                double* __restrict__ xout,
