@@ -22,6 +22,16 @@ MGP_TP_ALL_T(MGP_TP_DECL, 1)
 MGP_TP_ALL_T(MGP_TP_DECL, 2)
 MGP_TP_ALL_T(MGP_TP_DECL, 3)
 #undef MGP_TP_DECL
+// ... and with the back substitution / gradient epilogue (T <= 8)
+#define MGP_TPG_DECL(F, T)                                                                  \
+  int launch_fused_tpg_f##F##_t##T(const mgp_problem*, const Model&, const ColLoo&, int*, \
+                                   cudaStream_t);
+#define MGP_TPG_ALL_T(X, F) X(F, 2) X(F, 3) X(F, 4) X(F, 5) X(F, 6) X(F, 7) X(F, 8)
+MGP_TPG_ALL_T(MGP_TPG_DECL, 0)
+MGP_TPG_ALL_T(MGP_TPG_DECL, 1)
+MGP_TPG_ALL_T(MGP_TPG_DECL, 2)
+MGP_TPG_ALL_T(MGP_TPG_DECL, 3)
+#undef MGP_TPG_DECL
 int launch_fused_colg_f0(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_colg_f1(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
 int launch_fused_colg_f2(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
@@ -64,34 +74,41 @@ int fused_col_supported(const mgp_problem* p, const Model& model) {
 static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& loo, int* grid_out,
                       cudaStream_t stream) {
   const int T = col_tiles(p->k);
-  // Back substitution wanted, or variant 4 (cross-check of the thread-per-tile kernel with the
-  // lane-parallel column kernel: its GRAD instantiation, whose back substitution then goes
-  // unused): fused_col_kernel<T, F, D, true>.
-  if (loo.grad != nullptr || loo.backsub || (fused_variant() == 4 && T <= COL_MAX_T)) {
+  typedef int (*launcher)(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+  const int f = col_formula(model);
+  MGP_REQUIRE(f >= 0 && f < 4 && T >= 2 && T <= TP_MAX_T, MGP_ERR_UNSUPPORTED,
+              "column kernels do not support this kernel / metric pair or k = %d", p->k);
+  const bool backsub = loo.grad != nullptr || loo.backsub;
+  if (backsub)
     MGP_REQUIRE(T <= COL_MAX_T, MGP_ERR_UNSUPPORTED,
                 "coefficients / analytic gradient: k = %d needs more than %d tile rows", p->k,
                 COL_MAX_T);
-    switch (col_formula(model)) {
+  // Variant 4 (cross-check of the thread-per-tile kernels): the lane-parallel column kernel,
+  // GRAD instantiation -- its back substitution goes unused for a plain prediction.
+  if (fused_variant() == 4 && T <= COL_MAX_T) {
+    switch (f) {
       case F_M05: return launch_fused_colg_f0(p, model, loo, grid_out, stream);
       case F_M15: return launch_fused_colg_f1(p, model, loo, grid_out, stream);
       case F_M25: return launch_fused_colg_f2(p, model, loo, grid_out, stream);
-      case F_GAUSS: return launch_fused_colg_f3(p, model, loo, grid_out, stream);
-      default:
-        set_error("column kernel does not support this kernel / metric pair");
-        return MGP_ERR_UNSUPPORTED;
+      default: return launch_fused_colg_f3(p, model, loo, grid_out, stream);
     }
   }
-  // Plain prediction and the one-launch objective: the thread-per-tile kernel (fused_tp.cuh)
-  typedef int (*launcher)(const mgp_problem*, const Model&, const ColLoo&, int*, cudaStream_t);
+  if (backsub) {
+#define MGP_TPG_ENTRY(F, TT) launch_fused_tpg_f##F##_t##TT,
+    static const launcher gtable[4][COL_MAX_T - 1] = {{MGP_TPG_ALL_T(MGP_TPG_ENTRY, 0)},
+                                                      {MGP_TPG_ALL_T(MGP_TPG_ENTRY, 1)},
+                                                      {MGP_TPG_ALL_T(MGP_TPG_ENTRY, 2)},
+                                                      {MGP_TPG_ALL_T(MGP_TPG_ENTRY, 3)}};
+#undef MGP_TPG_ENTRY
+    return gtable[f][T - 2](p, model, loo, grid_out, stream);
+  }
+  // Plain prediction and the one-launch objective
 #define MGP_TP_ENTRY(F, TT) launch_fused_tp_f##F##_t##TT,
   static const launcher table[4][TP_MAX_T - 1] = {{MGP_TP_ALL_T(MGP_TP_ENTRY, 0)},
                                                   {MGP_TP_ALL_T(MGP_TP_ENTRY, 1)},
                                                   {MGP_TP_ALL_T(MGP_TP_ENTRY, 2)},
                                                   {MGP_TP_ALL_T(MGP_TP_ENTRY, 3)}};
 #undef MGP_TP_ENTRY
-  const int f = col_formula(model);
-  MGP_REQUIRE(f >= 0 && f < 4 && T >= 2 && T <= TP_MAX_T, MGP_ERR_UNSUPPORTED,
-              "column kernels do not support this kernel / metric pair or k = %d", p->k);
   return table[f][T - 2](p, model, loo, grid_out, stream);
 }
 

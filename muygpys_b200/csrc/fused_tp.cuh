@@ -57,9 +57,18 @@ struct TpSlots {
   int count;
 };
 
-template <int T>
+// REUSE = false (back substitution wanted: the whole factor must survive): one slot per tile.
+template <int T, bool REUSE = true>
 constexpr TpSlots<T> tp_make_slots() {
   TpSlots<T> m{};
+  if (!REUSE) {
+    int n = 0;
+    for (int P = 0; P + 1 < T; ++P) m.s[T - 1][P] = n++;
+    for (int I = 1; I + 1 < T; ++I)
+      for (int P = 0; P < I; ++P) m.s[I][P] = n++;
+    m.count = n;
+    return m;
+  }
   int busy_until[T * T + 1] = {};  // slot -> tile row of its occupant (free again when <= P)
   int count = T - 1;
   for (int P = 0; P + 1 < T; ++P) m.s[T - 1][P] = P;
@@ -100,12 +109,15 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
 // per update warp, in doubles: finished tiles | -1/d | diagonal tile in | M out | outputs
 // (three Schur entries, ok) | 2 x points | 2 x targets; the stride is 2 (mod 16) doubles so that
 // the factor warp's lanes, which read one tile each, start in different banks
-template <int T>
+// GRAD adds: M_J of every tile column (accumulator order), the last two diagonal tiles after
+// their column steps, and the solution vectors w = K^-1 kcross, alpha = K^-1 y.
+template <int T, bool GRAD = false>
 static inline size_t tp_warp_doubles(int k, int d) {
-  constexpr TpSlots<T> SL = tp_make_slots<T>();
+  constexpr TpSlots<T> SL = tp_make_slots<T, !GRAD>();
   const size_t pts = (size_t)((((k + 1) * d) + 1) & ~1);
   const size_t ys = (size_t)((k + 2) & ~1);
-  size_t n = (size_t)SL.count * 64 + 8 * (size_t)T + 64 + 64 + 8 + 2 * pts + 2 * ys;
+  size_t n = (size_t)SL.count * 64 + 8 * (size_t)T + 64 + 64 + 8 + 2 * pts + 2 * ys +
+             (GRAD ? (size_t)(T + 2) * 64 + 16 * (size_t)T : 0);
   while ((n & 15) != 2) n += 2;
   return n;
 }
@@ -131,11 +143,14 @@ __device__ __forceinline__ double neg_rcp_fast(double p) {
 //   xo[3]        = 1 if every pivot was positive, finite and normal
 // FULL: all eight columns are eliminated (every tile column but the last two): no predicates, no
 // zero fill, nothing captured (xo[3] only).
+// xdiag (not FULL, may be null): the tile after its column steps, row-major lower triangle
+// (entries (i,j), j < ncols, are U = L D; the rest is the Schur complement).
 template <bool FULL>
 __device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
                                                double* __restrict__ xout,
                                                double* __restrict__ dinv,
-                                               double* __restrict__ xo, int ncols) {
+                                               double* __restrict__ xo, int ncols,
+                                               double* __restrict__ xdiag = nullptr) {
   double a[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -198,6 +213,12 @@ __device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
       *reinterpret_cast<double2*>(xout + 8 * c + r) = make_double2(lo, hi);
     }
   }
+  if (!FULL && xdiag != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) xdiag[8 * i + j] = a[i][j];
+  }
   if (FULL) {
     xo[3] = ok ? 1.0 : 0.0;
   } else {
@@ -206,15 +227,15 @@ __device__ __forceinline__ void tp_factor_tile(const double* __restrict__ xin,
   }
 }
 
-template <int T, int F, int D, int TP_UWARPS>
+template <int T, int F, int D, int TP_UWARPS, bool GRAD = false>
 __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     fused_tp_kernel(const TileArgs a, const ColLoo loo, int pts_doubles, int ys_doubles,
                     int warp_doubles, long long iters) {
   extern __shared__ double smem[];
   constexpr int TP_THREADS = (TP_UWARPS + 1) * 32;
-  constexpr TpSlots<T> SL = tp_make_slots<T>();
+  constexpr TpSlots<T> SL = tp_make_slots<T, !GRAD>();
   constexpr int W = 8 * (T - 1);
-  constexpr int NREC = MGP_PARTIALS;
+  constexpr int NREC = GRAD ? COL_NREC_GRAD : MGP_PARTIALS;
   __shared__ double s_acc[TP_UWARPS][NREC];
   for (int e = threadIdx.x; e < TP_UWARPS * NREC; e += blockDim.x) (&s_acc[0][0])[e] = 0.0;
   // MGP_TP_FACTOR_FIRST: the factor warp is warp 0 (the oldest warp of the CTA)
@@ -255,9 +276,11 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
           if (J <= T - 3)
             tp_factor_tile<true>(base + OFF_XIN, base + OFF_XOUT, base + OFF_DINV + 8 * J,
                                  base + OFF_XO, 8);
-          else
+          else  // (J = T - 2; GRAD keeps the tile for the back substitution: Dg[0])
             tp_factor_tile<false>(base + OFF_XIN, base + OFF_XOUT, base + OFF_DINV + 8 * J,
-                                  base + OFF_XO, ncols);
+                                  base + OFF_XO, ncols,
+                                  GRAD ? base + OFF_PTS + 2 * pts_doubles + 2 * ys_doubles + T * 64
+                                       : nullptr);
         }
         TP_TRACE(TP_UWARPS, 2 * J + 1);
         bar_arrive(2, TP_THREADS);
@@ -273,6 +296,10 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     const double* xo = Ls + OFF_XO;
     double* pts_buf = Ls + OFF_PTS;
     double* ys_buf = pts_buf + 2 * pts_doubles;
+    double* Ms = ys_buf + 2 * ys_doubles;  // GRAD: M_J = L_JJ^-T per tile column (accumulator order)
+    double* Dg = Ms + T * 64;              // GRAD: diagonal tiles T-2, T-1 after their steps
+    double* wv = Dg + 2 * 64;              // GRAD: w = K^-1 kcross (8 T entries)
+    double* av = wv + 8 * T;               // GRAD: alpha = K^-1 y
     const long long wglobal = (long long)blockIdx.x * TP_UWARPS + warp;
     const long long wstride = (long long)gridDim.x * TP_UWARPS;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -326,6 +353,8 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     // ---- results of one neighbourhood (called one pipeline stage after its last column) -----
     bool ok = true;
     double out_var = 0.0, out_mean = 0.0, out_yky = 0.0;
+    double gdm[4] = {0.0, 0.0, 0.0, 0.0}, gdv[4] = {0.0, 0.0, 0.0, 0.0},
+           gdy[4] = {0.0, 0.0, 0.0, 0.0};  // GRAD: d mean, d var, d yky per parameter
     auto write_outputs = [&](long long row, long long qs) {
       if (lane == 0 && row < a.b) {
         if (a.var) a.var[row] = ok ? a.scale * out_var : nan;
@@ -347,6 +376,20 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
               const double z = err / loo.boundary_scale;
               acc[MGP_P_AUX] +=
                   loo.boundary_scale * loo.boundary_scale * (sqrt(fma(z, z, 1.0)) - 1.0);
+            }
+            if (GRAD) {
+              const double iv = 1.0 / out_var;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (t < D || t == 3) {
+                  double* gr = acc + MGP_PARTIALS + 5 * t;
+                  gr[0] += 2.0 * err * gdm[t];        // d sum e^2
+                  gr[1] += 2.0 * err * gdm[t] * iv;   // sum 2 e dm / v
+                  gr[2] += e2 * gdv[t] * iv * iv;     // sum e^2 dv / v^2
+                  gr[3] += gdv[t] * iv;               // sum dv / v
+                  gr[4] += gdy[t];                    // d sum yky
+                }
+              }
             }
           } else {
             acc[MGP_P_BAD] += 1.0;
@@ -512,6 +555,8 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       constexpr int J = T - 1;
       const int ncols = max(0, min(8, k - 8 * J));
       const int qb = lane & ~3;
+      double v0 = (rho == 2 * q) ? 1.0 : 0.0, v1 = (rho == 2 * q + 1) ? 1.0 : 0.0;  // GRAD: M
+      double di0 = 0.0, di1 = 0.0;                                                 // GRAD: 1/d
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         if (j < ncols) {
@@ -527,7 +572,18 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
           const double t1 = sel_d(2 * q + 1 > j, uc1, 0.0) * pinv;
           c[J][0] = fma(-lr, t0, c[J][0]);
           c[J][1] = fma(-lr, t1, c[J][1]);
+          if (GRAD) {
+            const double vr = shfl_d(bj == 0 ? v0 : v1, qb | qj);  // V[row][j]
+            v0 = fma(-vr, t0, v0);
+            v1 = fma(-vr, t1, v1);
+            if (bj == 0) di0 = sel_d(q == qj, pinv, di0); else di1 = sel_d(q == qj, pinv, di1);
+          }
         }
+      }
+      if (GRAD) {
+        if (rho == 0) *reinterpret_cast<double2*>(dinv_s + 8 * J + 2 * q) = make_double2(-di0, -di1);
+        *reinterpret_cast<double2*>(Ms + J * 64 + 2 * lane) = make_double2(v0, v1);
+        *reinterpret_cast<double2*>(Dg + 64 + 2 * lane) = make_double2(c[J][0], c[J][1]);
       }
       if (kl < 7) {
         const double cv = (kl & 1) ? c[J][1] : c[J][0];
@@ -548,6 +604,9 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       if (J + 1 >= T) return;
       const double2 bm = *reinterpret_cast<const double2*>(Xout + 2 * lane);
       const double2 nd = *reinterpret_cast<const double2*>(dinv_s + 8 * J + 2 * q);
+      if (GRAD)  // Xout is column-major (B-fragment order): M[rho][2q], M[rho][2q+1]
+        *reinterpret_cast<double2*>(Ms + J * 64 + 2 * lane) =
+            make_double2(Xout[16 * q + rho], Xout[16 * q + 8 + rho]);
       double n0[T], n1[T];
       double2 raw[T];
 #pragma unroll
@@ -614,13 +673,15 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     //     start the staging of the neighbourhood after `nx`; first tile pair of column 0
     long long q_next = 0;
     constexpr int FIRST = (T >= 3) ? 2 : 0;  // T >= 3: the first tile pair of column 0 is regular
-    auto prep_stage_and_first = [&](long long nx, int nbuf) {
+    auto prep_stage = [&](long long nx, int nbuf) {
       const long long row = wglobal + nx * wstride;
       __syncwarp();  // every lane has read what it needed from the buffer about to be refilled
       q_next = query_of_staged();  // query of row nx + 1
       issue_all(nbuf ^ 1);
       cp_async_commit();
       load_all(row + 2 * wstride);
+    };
+    auto prep_first = [&](int nbuf) {
       if (FIRST)
         build_column(0, 0, pts_buf + nbuf * pts_doubles, ys_buf + nbuf * ys_doubles, 0, FIRST);
     };
@@ -658,12 +719,185 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       }
     };
 
+    // ---- back substitution and analytic gradient (GRAD; same algebra as fused_col_kernel) ------
+    // w = K^-1 kcross and alpha = K^-1 y from a block back substitution on the stored factor;
+    // alpha is the fast-mean coefficient row.  Gradient of (mean, variance, y^T K^-1 y) w.r.t.
+    // length scale(s) and nugget: d mean = dc^T alpha - w^T dK alpha, d var = -2 dc^T w +
+    // w^T dK w, d yky = -alpha^T dK alpha, with dK_ij / dl_f = phi(s_ij) z_f^2 / l_f re-evaluated
+    // entry by entry (never stored).
+    auto grad_epilogue = [&](const double* pts, long long row) {
+      const int Jlast = (k - 1) >> 3;            // last tile column that holds K columns
+      const int Rk = k >> 3, Ry = (k + 1) >> 3;  // tile rows of the cross row and the target row
+      const int ly = (k + 1) & 7;
+      __syncwarp();
+      for (int e = lane; e < 8 * T; e += 32) {
+        wv[e] = 0.0;
+        av[e] = 0.0;
+      }
+      __syncwarp();
+      double xw[T], xa[T];  // this lane's row (rho) of the solution blocks
+#pragma unroll
+      for (int I = 0; I < T; ++I) xw[I] = xa[I] = 0.0;
+      // tile (row tile R, column tile J2) as stored: finished tile, or final diagonal tile
+      auto stored = [&](int R, int J2, int off) -> double2 {
+        const double* base = (J2 < R) ? Ls + slot_off(R, J2) : Dg + (R - (T - 2)) * 64;
+        return *reinterpret_cast<const double2*>(base + off);
+      };
+#pragma unroll
+      for (int J = T - 1; J >= 0; --J) {
+        if (J <= Jlast) {
+          const int nc = min(8, k - 8 * J);  // eliminated columns of this tile column
+          double ac0 = 0.0, ac1 = 0.0, ay0 = 0.0, ay1 = 0.0;
+#pragma unroll
+          for (int I = J + 1; I < T; ++I) {
+            if (I <= Jlast) {
+              const double2 u = *reinterpret_cast<const double2*>(Ls + slot_off(I, J) + 2 * lane);
+              ac0 = fma(u.x, xw[I], ac0);
+              ac1 = fma(u.y, xw[I], ac1);
+              ay0 = fma(u.x, xa[I], ay0);
+              ay1 = fma(u.y, xa[I], ay1);
+            }
+          }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {  // sum over the 8 rows (lanes with the same q)
+            ac0 += __shfl_xor_sync(0xffffffffu, ac0, o);
+            ac1 += __shfl_xor_sync(0xffffffffu, ac1, o);
+            ay0 += __shfl_xor_sync(0xffffffffu, ay0, o);
+            ay1 += __shfl_xor_sync(0xffffffffu, ay1, o);
+          }
+          // (Rk, Ry >= T - 2: rows k, k + 1 of U sit in the last two tile rows)
+          double2 zc = make_double2(0.0, 0.0), zy = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int R = (T >= 2 ? T - 2 : 0); R < T; ++R) {
+            if (R == Rk && J <= R) zc = stored(R, J, kl * 8 + 2 * q);
+            if (R == Ry && J <= R) zy = stored(R, J, ly * 8 + 2 * q);
+          }
+          const double2 nd = *reinterpret_cast<const double2*>(dinv_s + 8 * J + 2 * q);
+          const bool in0 = 2 * q < nc, in1 = 2 * q + 1 < nc;
+          const double sc0 = in0 ? (ac0 - zc.x) * nd.x : 0.0, sc1 = in1 ? (ac1 - zc.y) * nd.y : 0.0;
+          const double sy0 = in0 ? (ay0 - zy.x) * nd.x : 0.0, sy1 = in1 ? (ay1 - zy.y) * nd.y : 0.0;
+          // x_J = L_JJ^-T D^-1 t = M_J (D^-1 t): row rho, summed over the quad
+          const double2 m = *reinterpret_cast<const double2*>(Ms + J * 64 + 2 * lane);
+          double vw = fma(m.x, sc0, m.y * sc1), va = fma(m.x, sy0, m.y * sy1);
+          vw += __shfl_xor_sync(0xffffffffu, vw, 1);
+          va += __shfl_xor_sync(0xffffffffu, va, 1);
+          vw += __shfl_xor_sync(0xffffffffu, vw, 2);
+          va += __shfl_xor_sync(0xffffffffu, va, 2);
+          xw[J] = (rho < nc) ? vw : 0.0;
+          xa[J] = (rho < nc) ? va : 0.0;
+          if (q == 0) {
+            wv[8 * J + rho] = xw[J];
+            av[8 * J + rho] = xa[J];
+          }
+        }
+      }
+      __syncwarp();
+      // fast-mean precompute mode: alpha = (K + eps)^-1 y IS the coefficient row
+      // (S/_src/gp/muygps/numpy.py:88-95)
+      if (a.coeffs && row < a.b)  // (rows past the end of the batch repeat the last row)
+        for (int e = lane; e < k; e += 32) a.coeffs[row * k + e] = ok ? av[e] : nan;
+      if (loo.grad == nullptr) return;
+      // weighted re-evaluation: per tile row I the row-factored sums
+      //   Ra_f = sum_j phi z_f^2 alpha_j,  Rw_f = sum_j phi z_f^2 w_j   (j over tile columns <= I)
+      double Gm[D], Gv[D], Gy[D];
+#pragma unroll
+      for (int f = 0; f < D; ++f) Gm[f] = Gv[f] = Gy[f] = 0.0;
+#pragma unroll
+      for (int I = 0; I < T; ++I) {
+        if (I <= Jlast) {
+          const Pt<D> pr = ld_pt<D>(pts, min(8 * I + rho, k));
+          double Ra[D], Rw[D];
+#pragma unroll
+          for (int f = 0; f < D; ++f) Ra[f] = Rw[f] = 0.0;
+          auto tile_pair = [&](int Ja, int Jb, bool two) {
+            const Pt<D> a0 = ld_pt<D>(pts, min(8 * Ja + 2 * q, k)),
+                        a1 = ld_pt<D>(pts, min(8 * Ja + 2 * q + 1, k));
+            const Pt<D> b0 = ld_pt<D>(pts, min(8 * Jb + 2 * q, k)),
+                        b1 = ld_pt<D>(pts, min(8 * Jb + 2 * q + 1, k));
+            const double2 wa = *reinterpret_cast<const double2*>(wv + 8 * Ja + 2 * q);
+            const double2 aa = *reinterpret_cast<const double2*>(av + 8 * Ja + 2 * q);
+            const double2 wb = *reinterpret_cast<const double2*>(wv + 8 * Jb + 2 * q);
+            const double2 ab = *reinterpret_cast<const double2*>(av + 8 * Jb + 2 * q);
+            const Pt<D>* pc[4] = {&a0, &a1, &b0, &b1};
+            const double wj[4] = {wa.x, wa.y, wb.x, wb.y}, aj[4] = {aa.x, aa.y, ab.x, ab.y};
+            const double half[4] = {Ja == I ? 0.5 : 1.0, Ja == I ? 0.5 : 1.0,
+                                    Jb == I ? 0.5 : 1.0, Jb == I ? 0.5 : 1.0};
+            double u[4], ph[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) u[e] = sq_dist<D>(pr, *pc[e]);
+            cov_n<F, 4, 1>(u, tab64, ph);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (e < 2 || two) {
+                const double pe = ph[e] * half[e];
+#pragma unroll
+                for (int f = 0; f < D; ++f) {
+                  const double df = pr.x[f] - pc[e]->x[f];
+                  const double g = pe * (df * df);
+                  Ra[f] = fma(g, aj[e], Ra[f]);
+                  Rw[f] = fma(g, wj[e], Rw[f]);
+                }
+              }
+            }
+          };
+#pragma unroll
+          for (int Ja = 0; Ja <= I; Ja += 2) tile_pair(Ja, (Ja + 1 <= I) ? Ja + 1 : Ja, Ja + 1 <= I);
+#pragma unroll
+          for (int f = 0; f < D; ++f) {
+            Gm[f] = fma(xw[I], Ra[f], fma(xa[I], Rw[f], Gm[f]));
+            Gv[f] = fma(2.0 * xw[I], Rw[f], Gv[f]);
+            Gy[f] = fma(2.0 * xa[I], Ra[f], Gy[f]);
+          }
+        }
+      }
+      // cross-covariance row: dc_j / dl_f = phi(s_qj) z_f^2 / l_f
+      double Gmc[D], Gvc[D];
+#pragma unroll
+      for (int f = 0; f < D; ++f) Gmc[f] = Gvc[f] = 0.0;
+      {
+        const Pt<D> pq = ld_pt<D>(pts, k);
+        const int ja = min(lane, k), jb = min(lane + 32, k);
+        const Pt<D> p0 = ld_pt<D>(pts, ja), p1 = ld_pt<D>(pts, jb);
+        const double u[2] = {sq_dist<D>(pq, p0), sq_dist<D>(pq, p1)};
+        double ph[2];
+        cov_n<F, 2, 1>(u, tab64, ph);
+        const double w0 = lane < k ? wv[ja] : 0.0, a0 = lane < k ? av[ja] : 0.0;
+        const double w1 = lane + 32 < k ? wv[jb] : 0.0, a1 = lane + 32 < k ? av[jb] : 0.0;
+#pragma unroll
+        for (int f = 0; f < D; ++f) {
+          const double d0 = pq.x[f] - p0.x[f], d1 = pq.x[f] - p1.x[f];
+          const double g0 = ph[0] * (d0 * d0), g1 = ph[1] * (d1 * d1);
+          Gmc[f] = fma(g0, a0, fma(g1, a1, Gmc[f]));
+          Gvc[f] = fma(g0, w0, fma(g1, w1, Gvc[f]));
+        }
+      }
+      // nugget: dK = I
+      double dwa = 0.0, dww = 0.0, daa = 0.0;
+      for (int e = lane; e < 8 * T; e += 32) {
+        dwa = fma(wv[e], av[e], dwa);
+        dww = fma(wv[e], wv[e], dww);
+        daa = fma(av[e], av[e], daa);
+      }
+#pragma unroll
+      for (int f = 0; f < D; ++f) {
+        const double rm = warp_sum(Gm[f]), rv = warp_sum(Gv[f]), ry = warp_sum(Gy[f]);
+        const double rmc = warp_sum(Gmc[f]), rvc = warp_sum(Gvc[f]);
+        gdm[f] = (rmc - rm) * loo.inv_len[f];
+        gdv[f] = (rv - 2.0 * rvc) * loo.inv_len[f];
+        gdy[f] = -ry * loo.inv_len[f];
+      }
+      gdm[3] = -warp_sum(dwa);
+      gdv[3] = warp_sum(dww);
+      gdy[3] = -warp_sum(daa);
+    };
+
     // Software pipeline, one stage per tile column: while the factor warp works on the
     // diagonal tile of column J, this warp builds column J + 1.
     int buf = 0;
     if (iters > 0) {
       prep_scale(0);
-      prep_stage_and_first(0, 0);
+      prep_stage(0, 0);
+      prep_first(0);
     }
     constexpr int J_SCALE = (T >= 3) ? T - 3 : 0;  // stage that hosts piece (1) of the next one
     for (it = 0; it < iters; ++it, buf ^= 1) {
@@ -688,8 +922,12 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       for (int J = 0; J + 1 < T; ++J) {
         build_column(J + 1, J, pts, ys);
         if (J == J_SCALE && more) prep_scale(buf ^ 1);
-        // column T - 1 is built: c[0 .. T-2] and this neighbourhood's staging buffer are free
-        if (J == T - 2 && more) prep_stage_and_first(it + 1, buf ^ 1);
+        // column T - 1 is built: c[0 .. T-2] and -- unless the gradient pass re-evaluates the
+        // entries -- this neighbourhood's staging buffer are free
+        if (J == T - 2 && more) {
+          if (!GRAD) prep_stage(it + 1, buf ^ 1);
+          prep_first(buf ^ 1);
+        }
         TP_TRACE(warp, 4 * J + 4);
         bar_sync(2, TP_THREADS);
         TP_TRACE(warp, 4 * J + 5);
@@ -699,6 +937,10 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       }
       if (T == 1) c[0][0] = c[0][1] = 0.0;  // (not instantiated)
       last_column();
+      if (GRAD) {
+        grad_epilogue(pts, row);
+        if (more) prep_stage(it + 1, buf ^ 1);
+      }
       write_outputs(row, q_src);
       q_src = q_after;
     }
@@ -709,7 +951,7 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     // fixed-order reduction, as in fused_col_kernel: update warps of a block -> block record ->
     // (last block) strided partial sums -> sequential sum; then the cross-GPU exchange
     __shared__ unsigned int s_last;
-    constexpr int NGRP = 16;
+    constexpr int NGRP = (TP_THREADS / NREC) < 16 ? (TP_THREADS / NREC) : 16;
     __shared__ double s_red[NGRP][NREC];
     __syncthreads();
     if (threadIdx.x < NREC) {
@@ -737,8 +979,13 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
         double tot = 0.0;
 #pragma unroll
         for (int g = 0; g < NGRP; ++g) tot += s_red[g][threadIdx.x];
-        s_tot[threadIdx.x] = tot;
-        if (loo.peers.world <= 1) loo.partials[threadIdx.x] = tot;
+        if (threadIdx.x < MGP_PARTIALS) {
+          s_tot[threadIdx.x] = tot;
+          if (loo.peers.world <= 1) loo.partials[threadIdx.x] = tot;
+        } else if (GRAD && loo.grad != nullptr &&
+                   threadIdx.x < MGP_PARTIALS + MGP_GRAD_DOUBLES) {
+          loo.grad[threadIdx.x - MGP_PARTIALS] = tot;
+        }
       }
       if (threadIdx.x == 0) *loo.counter = 0u;
       if (loo.peers.world > 1) {
@@ -750,16 +997,16 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
 }
 
 // ---- host side --------------------------------------------------------------------------
-template <int T, int F, int D, int U>
+template <int T, int F, int D, int U, bool GRAD = false>
 int launch_tp_inst(const TileArgs& a, const ColLoo& loo, long long rows, int* grid_out,
                    cudaStream_t stream) {
   constexpr int THREADS = (U + 1) * 32;
   const int pts_doubles = (((a.k + 1) * D) + 1) & ~1;
   const int ys_doubles = (a.k + 2) & ~1;
-  const size_t warp_doubles = tp_warp_doubles<T>(a.k, D);
+  const size_t warp_doubles = tp_warp_doubles<T, GRAD>(a.k, D);
   const size_t smem = warp_doubles * U * sizeof(double);
   cudaFuncAttributes fa;
-  MGP_REQUIRE(cudaFuncGetAttributes(&fa, fused_tp_kernel<T, F, D, U>) == cudaSuccess,
+  MGP_REQUIRE(cudaFuncGetAttributes(&fa, fused_tp_kernel<T, F, D, U, GRAD>) == cudaSuccess,
               MGP_ERR_CUDA, "cudaFuncGetAttributes failed");
   const size_t smem_cap = (size_t)max_smem_optin() - fa.sharedSizeBytes;
   MGP_REQUIRE(smem <= smem_cap, MGP_ERR_UNSUPPORTED,
@@ -768,8 +1015,8 @@ int launch_tp_inst(const TileArgs& a, const ColLoo& loo, long long rows, int* gr
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(fused_tp_kernel<T, F, D, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem_cap);
+    cudaFuncSetAttribute(fused_tp_kernel<T, F, D, U, GRAD>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     attr_set[dev] = true;
   }
   // one CTA per SM (launch bounds); every update warp of a CTA runs the same number of
@@ -783,30 +1030,32 @@ int launch_tp_inst(const TileArgs& a, const ColLoo& loo, long long rows, int* gr
     *grid_out = (int)blocks;
   }
   const long long iters = (rows + blocks * U - 1) / (blocks * U);
-  fused_tp_kernel<T, F, D, U><<<(unsigned)blocks, THREADS, smem, stream>>>(
+  fused_tp_kernel<T, F, D, U, GRAD><<<(unsigned)blocks, THREADS, smem, stream>>>(
       a, loo, pts_doubles, ys_doubles, (int)warp_doubles, iters);
   return check_launch("fused_tp_kernel");
 }
 
 // Update warps per CTA: as many as shared memory holds for the largest k of this T (8 T - 2), at
 // most TP_MAX_UWARPS; T = 9 is capped at 11 so that the CTA has 12 warps -- three per scheduler,
-// 168 registers per thread (its tile column and B fragments do not fit in 128).
+// 168 registers per thread (its tile column and B fragments do not fit in 128).  The same cap
+// holds for every GRAD instantiation (back substitution and gradient pass need the registers).
 constexpr int TP_MAX_T = 13;
-template <int T, int D>
+template <int T, int D, bool GRAD = false>
 constexpr int tp_uwarps() {
   constexpr int k = 8 * T - 2;
   constexpr size_t pts = (size_t)((((k + 1) * D) + 1) & ~1), ys = (size_t)((k + 2) & ~1);
-  size_t n = (size_t)tp_make_slots<T>().count * 64 + 8 * (size_t)T + 64 + 64 + 8 + 2 * pts + 2 * ys;
+  size_t n = (size_t)tp_make_slots<T, !GRAD>().count * 64 + 8 * (size_t)T + 64 + 64 + 8 +
+             2 * pts + 2 * ys + (GRAD ? (size_t)(T + 2) * 64 + 16 * (size_t)T : 0);
   while ((n & 15) != 2) n += 2;
   int u = (int)((227 * 1024 - 4096) / (n * sizeof(double)));
-  if (T == 9 && u > 11) u = 11;
+  if ((T == 9 || GRAD) && u > 11) u = 11;
   return u > TP_MAX_UWARPS ? TP_MAX_UWARPS : u;
 }
 
-template <int T, int F, int D>
+template <int T, int F, int D, bool GRAD = false>
 int launch_tp_one(const TileArgs& a, const ColLoo& loo, long long rows, int* grid_out,
                   cudaStream_t stream) {
-  return launch_tp_inst<T, F, D, tp_uwarps<T, D>()>(a, loo, rows, grid_out, stream);
+  return launch_tp_inst<T, F, D, tp_uwarps<T, D, GRAD>(), GRAD>(a, loo, rows, grid_out, stream);
 }
 
 }  // namespace
