@@ -132,19 +132,21 @@ int mgp_fused_posterior(const mgp_problem* p, void* ws, size_t ws_bytes, void* s
  * HOST memory, results wanted in host memory.  `p` is filled as for mgp_fused_posterior, with
  * p->nn_idx (b*k) and, if query_idx_host is given, p->query_idx (b) pointing at DEVICE staging
  * buffers that this call fills; mean_host / var_host (nullable) receive copies of p->mean /
- * p->var.  The batch is processed in chunks on two internal streams so that the upload of
- * chunk c+1 and the download of chunk c-1 overlap the kernel of chunk c; the work is ordered
+ * p->var.  The batch is processed in chunks on three internal streams (upload, kernel,
+ * download, linked by one event per chunk) so that the upload of chunk c+1 and the download of
+ * chunk c-1 overlap the kernel of chunk c and the uploads run back to back; the work is ordered
  * after `stream` and joined back into it (synchronise `stream` before reading the host
  * results).  Host buffers should be page-locked for the copies to overlap. */
 int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_idx_host,
                              const int64_t* query_idx_host, double* mean_host,
                              double* var_host, void* ws, size_t ws_bytes, void* stream);
 
-/* Test/bench hook: 0 = choose automatically (column-direct > tile > generic), 1 = always the
+/* Test/bench hook: 0 = choose automatically (thread-per-tile > tile > generic), 1 = always the
  * generic shared-memory kernel, 2 = the register-tile DMMA kernel where supported, 3 = the
- * column-direct kernels (error if the shape is unsupported), 4 = the column-direct kernel with
- * lane-parallel column steps even where the thread-per-tile kernel would be taken.  Lets the
- * independently written variants be cross-checked on identical inputs. */
+ * thread-per-tile kernel (error if the shape is unsupported: r == 1, d <= 3, homoscedastic
+ * nugget, 7 <= k <= 102; <= 62 with coefficients), 4 = its lane-parallel predecessor, the
+ * column-direct kernel (k <= 62).  Lets the independently written variants be cross-checked on
+ * identical inputs. */
 int mgp_set_fused_variant(int32_t variant);
 
 /* One leave-one-out objective evaluation in ONE launch (a14-a16): the fused kernel over a
@@ -158,7 +160,7 @@ int mgp_set_fused_variant(int32_t variant);
  * sequence (S/optimize/objective.py:20-105, S/_src/optimize/loss/numpy.py:22-61,
  * S/_src/optimize/scale/numpy.py:9-15) for mse, lool and pseudo-Huber (MGP_LOSS_NONE gives the
  * scale partials only); looph is nonlinear in the analytic scale and keeps the two-pass path
- * (mgp_fused_posterior + mgp_loss_partials).  r == 1, d <= 3, 7 <= k <= 62, homoscedastic nugget
+ * (mgp_fused_posterior + mgp_loss_partials).  r == 1, d <= 3, 7 <= k <= 102, homoscedastic nugget
  * (MGP_ERR_UNSUPPORTED otherwise).  `ws` must be ZERO-FILLED before its first use and handed
  * back unchanged afterwards (it carries a self-resetting arrival counter). */
 size_t mgp_fused_loo_workspace_bytes(const mgp_problem* p);
@@ -204,7 +206,7 @@ int mgp_fused_loo_peers(const mgp_problem* p, int32_t loss_id, double boundary_s
  *   grad[5t+4] = sum d yky                                   -> d sigma^2 (analytic scale)
  * from which the host finishes d mse and d lool (muygpys_b200/objective.py).  grad == NULL is
  * mgp_fused_loo_peers.  The gradient sums are per rank: `partials` goes through the peer
- * exchange, `grad` is summed across ranks by the caller. */
+ * exchange, `grad` is summed across ranks by the caller.  With grad != NULL: k <= 62. */
 int mgp_fused_loo_grad(const mgp_problem* p, int32_t loss_id, double boundary_scale,
                        double* partials, double* grad, void* ws, size_t ws_bytes,
                        const mgp_peer_group* g, void* stream);
