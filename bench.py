@@ -521,7 +521,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     clocks = sampler.stop(keep_loaded)
-    e2e_ms_per_step = allmax(sum(a.elapsed_time(b) for a, b in e_evs) / args.steps)
+    e2e_steps_ms = [a.elapsed_time(b) for a, b in e_evs]
+    e2e_ms_per_step = allmax(sum(e2e_steps_ms) / args.steps)
     e2e_knn_ms = timed_ms(step_e2e_knn, max(5, args.steps // 2), warm=3)
     # what the host link of this box gives for the same pinned index buffer (explains e2e)
     nn_stage = torch.empty_like(nn)
@@ -812,6 +813,9 @@ def run_ours(args):
             "config": config_dict(world), "setup": setup,
             "e2e": {"value": world * N_TEST / (e2e_ms_per_step * 1e-3),
                     "unit": "neighbourhoods/s", "ms_per_step": e2e_ms_per_step,
+                    # (rank 0's individual steps: the host enqueues ~70 copies / launches /
+                    # events per step, so host jitter shows up here and not in `value`)
+                    "ms_steps_rank0": [round(t, 4) for t in e2e_steps_ms],
                     "h2d_bytes_per_step": int(N_TEST * D * 8 + N_TEST * K * 8 + N_TEST * 8),
                     "d2h_bytes_per_step": int(2 * N_TEST * 8),
                     "h2d_link_gbs": h2d_gbs,
@@ -827,7 +831,7 @@ def run_ours(args):
                              "api": "muygpys_b200.examples.regress.regress_any: pinned host test "
                                     "FEATURES in, exact KNN on the device, fused kernel, mean/var "
                                     "out -- the neighbour indices never cross the host link"},
-            "gpu_launches": args.steps,  # one fused_col_kernel launch per timed step per rank
+            "gpu_launches": args.steps,  # one fused_tp_kernel launch per timed step per rank
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
