@@ -182,17 +182,18 @@ __global__ void knn_grid_kernel(const GridArgs g) {
 //     key is the acceptance threshold for the next shell (if one is needed: same stopping rule,
 //     same slack as above).
 // Same arithmetic, same key order, same stopping rule as grid_query_serial: bit-identical
-// results.  A list that would exceed GW_CAP entries (heavily clustered or duplicated data)
+// results.  A list that would exceed its capacity (heavily clustered or duplicated data)
 // sends the query through grid_query_serial on lane 0, with the list's memory as its heap.
-constexpr int GW_CAP = 512;    // candidate list entries per warp
-constexpr int GW_WARPS = 8;    // warps (queries) per CTA
+// candidate list entries per warp: 256 up to k = 64 (two thirds more warps per SM), 512 above
+constexpr int GW_WARPS = 4;    // warps (queries) per CTA
+constexpr int GW_BINS = 256;   // histogram bins of the selection
 constexpr int GW_MAX_K = 128;  // larger k: thread-per-query kernel
 
 __device__ __forceinline__ bool key_less(double da, int ia, double db, int ib) {
   return da < db || (da == db && ia < ib);
 }
 
-// ascending bitonic sort of the first P (power of two, <= GW_CAP) entries by (distance, row)
+// ascending bitonic sort of the first P (power of two, <= list capacity) entries by (distance, row)
 __device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int P, int lane) {
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -214,10 +215,158 @@ __device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int P, in
   }
 }
 
-template <int D>
+// Exact selection of the k smallest keys of the list's first `count` (> k) entries WITHOUT sorting
+// them: a most-significant-bits-first radix selection on the bit pattern of the distance (a
+// non-negative double orders like its 64-bit pattern).  Each pass maps the keys of the current
+// range [lo, hi] onto 256 buckets by a shift, histograms them with shared-memory atomics and
+// narrows the range to the bucket that holds rank k - 1; as soon as that bucket has at most 32
+// entries they are sorted by (distance, row) in registers and the k-th key read off.  The list
+// is then compacted in place to the k entries <= that key (order not preserved) and their
+// number is returned.  Returns -1, list untouched, if the range collapses to one distance with
+// more than 32 rows (massive duplicates): the caller sorts instead.
+__device__ __forceinline__ int warp_select_k(double* sd, int* si, int count, int k, int lane,
+                                              unsigned* hist, double& tau_d, int& tau_i) {
+  typedef unsigned long long u64;
+  u64 lo = ~0ull, hi = 0ull;
+  for (int i = lane; i < count; i += 32) {
+    const u64 key = (u64)__double_as_longlong(sd[i]);
+    lo = key < lo ? key : lo;
+    hi = key > hi ? key : hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const u64 l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  int want = k - 1;  // rank (0-based) of the wanted key among the entries in [lo, hi]
+  int m = count;     // entries in [lo, hi]
+  for (int pass = 0; pass < 12 && m > 32; ++pass) {
+    const u64 range = hi - lo;
+    if (range == 0) return -1;
+    const int bits = 64 - __clzll((long long)range);  // range < 2^bits
+    const int shift = bits > 8 ? bits - 8 : 0;
+    for (int b = lane; b < GW_BINS; b += 32) hist[b] = 0;
+    __syncwarp();
+    for (int i = lane; i < count; i += 32) {
+      const u64 key = (u64)__double_as_longlong(sd[i]);
+      if (key >= lo && key <= hi) atomicAdd(&hist[(unsigned)((key - lo) >> shift)], 1u);
+    }
+    __syncwarp();
+    // lane l owns bins 8 l .. 8 l + 7
+    unsigned mine[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mine[j] = hist[8 * lane + j];
+      tot += mine[j];
+    }
+    unsigned incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned excl = incl - tot;
+    const bool here = (unsigned)want >= excl && (unsigned)want < incl;
+    int bin = -1;
+    unsigned before = 0, inbin = 0;
+    if (here) {
+      unsigned acc = excl;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (bin < 0 && (unsigned)want < acc + mine[j]) {
+          bin = 8 * lane + j;
+          before = acc;
+          inbin = mine[j];
+        }
+        acc += mine[j];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    before = __shfl_sync(0xffffffffu, before, src);
+    inbin = __shfl_sync(0xffffffffu, inbin, src);
+    want -= (int)before;
+    m = (int)inbin;
+    const u64 nlo = lo + ((u64)bin << shift);
+    const u64 nhi = nlo + (((u64)1 << shift) - 1);
+    lo = nlo;
+    hi = nhi < hi ? nhi : hi;
+    __syncwarp();
+  }
+  if (m > 32) return -1;
+  // the (at most 32) entries of the final range, one per lane (through the histogram's memory),
+  // sorted by (distance, row)
+  double* scr_d = reinterpret_cast<double*>(hist);       // 32 doubles
+  int* scr_i = reinterpret_cast<int*>(hist + 64);         // 32 ints behind them
+  int got = 0;
+  for (int i0 = 0; i0 < count; i0 += 32) {
+    const int i = i0 + lane;
+    bool in = false;
+    double s = 0.0;
+    if (i < count) {
+      s = sd[i];
+      const u64 key = (u64)__double_as_longlong(s);
+      in = key >= lo && key <= hi;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const int pos = got + __popc(mask & ((1u << lane) - 1));
+      scr_d[pos] = s;
+      scr_i[pos] = si[i];
+    }
+    got += __popc(mask);
+  }
+  __syncwarp();
+  double ms = lane < got ? scr_d[lane] : DBL_MAX;
+  int mi = lane < got ? scr_i[lane] : INT_MAX;
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const double os = __shfl_xor_sync(0xffffffffu, ms, stride);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, stride);
+      const bool lower = (lane & stride) == 0;          // this lane keeps the smaller key ...
+      const bool up = (lane & size) == 0;               // ... in ascending runs
+      const bool other_less = key_less(os, oi, ms, mi);
+      if (other_less == (lower == up)) {
+        ms = os;
+        mi = oi;
+      }
+    }
+  }
+  tau_d = __shfl_sync(0xffffffffu, ms, want);
+  tau_i = __shfl_sync(0xffffffffu, mi, want);
+  // compact the list in place to the entries <= tau (exactly k: the keys are distinct)
+  int out = 0;
+  for (int i0 = 0; i0 < count; i0 += 32) {
+    const int i = i0 + lane;
+    double s = 0.0;
+    int id = 0;
+    bool keep = false;
+    if (i < count) {
+      s = sd[i];
+      id = si[i];
+      keep = !key_less(tau_d, tau_i, s, id);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) {
+      const int pos = out + __popc(mask & ((1u << lane) - 1));
+      sd[pos] = s;
+      si[pos] = id;
+    }
+    out += __popc(mask);
+    __syncwarp();
+  }
+  return out;
+}
+
+template <int D, int GW_CAP>
 __global__ void __launch_bounds__(GW_WARPS * 32) knn_grid_warp_kernel(const GridArgs g) {
   __shared__ double s_d[GW_WARPS][GW_CAP];
   __shared__ int s_i[GW_WARPS][GW_CAP];
+  __shared__ __align__(16) unsigned s_hist[GW_WARPS][GW_BINS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long t = blockIdx.x * (long long)GW_WARPS + warp;
   if (t >= g.q) return;
@@ -325,8 +474,19 @@ __global__ void __launch_bounds__(GW_WARPS * 32) knn_grid_warp_kernel(const Grid
     scanned = r;
     if (overflow) break;
     __syncwarp();
-    if (count > k || !full) {
-      // sort, keep the k best; the k-th key is the new threshold
+    bool selected = false;
+    if (count > k) {
+      // the k best by exact selection; the k-th key is the new threshold
+      const int kept = warp_select_k(sd, si, count, k, lane, s_hist[warp], tau_d, tau_i);
+      if (kept >= 0) {
+        selected = true;
+        count = kept;  // (== k: the keys are distinct)
+        full = true;
+      }
+      __syncwarp();
+    }
+    if (!selected && (count > k || !full)) {
+      // (few candidates, or a distance shared by many rows): sort, keep the k best
       int P = 2;
       while (P < count) P <<= 1;
       for (int i = count + lane; i < P; i += 32) {
@@ -371,6 +531,17 @@ __global__ void __launch_bounds__(GW_WARPS * 32) knn_grid_warp_kernel(const Grid
     return;
   }
   __syncwarp();
+  {
+    // the list holds the answer; order it by (distance, row)
+    int P = 2;
+    while (P < count) P <<= 1;
+    for (int i = count + lane; i < P; i += 32) {
+      sd[i] = DBL_MAX;
+      si[i] = INT_MAX;
+    }
+    __syncwarp();
+    warp_bitonic_sort(sd, si, P, lane);
+  }
   for (int i = lane; i < k; i += 32) {
     g.out_idx[qi * k + i] = i < count ? si[i] : INT_MAX;
     g.out_d2[qi * k + i] = i < count ? sd[i] : DBL_MAX;
@@ -379,15 +550,17 @@ __global__ void __launch_bounds__(GW_WARPS * 32) knn_grid_warp_kernel(const Grid
 
 template <int D>
 static int launch_grid(const GridArgs& g, cudaStream_t s) {
-  // Small batches are latency-bound in the thread-per-query kernel (100 k queries are two
-  // thirds of one wave of threads): a warp per query is 2.5x faster at 10 k queries (k = 101),
-  // 7 % at 100 k, and 13 % SLOWER at 1 M, where the thread-per-query kernel has enough threads
-  // and does less work per query (no sorting network).  MGP_KNN_GRID = thread | warp overrides.
+  // A warp per query is 3.6x faster than a thread per query at 10 k queries (k = 101: the
+  // thread-per-query kernel is latency-bound there), 1.45x at 100 k and 1.25x at 1 M (k = 50).
+  // MGP_KNN_GRID = thread | warp overrides (dev switch).
   static const char* force = getenv("MGP_KNN_GRID");
-  const bool warp_per_query = force ? force[0] == 'w' : g.q <= 200000;
+  const bool warp_per_query = force ? force[0] == 'w' : true;
   if (g.k <= GW_MAX_K && warp_per_query) {
     const unsigned blocks = (unsigned)((g.q + GW_WARPS - 1) / GW_WARPS);
-    knn_grid_warp_kernel<D><<<blocks, GW_WARPS * 32, 0, s>>>(g);
+    if (g.k <= 64)
+      knn_grid_warp_kernel<D, 256><<<blocks, GW_WARPS * 32, 0, s>>>(g);
+    else
+      knn_grid_warp_kernel<D, 512><<<blocks, GW_WARPS * 32, 0, s>>>(g);
     return check_launch("knn_grid_warp_kernel");
   }
   // threads per CTA: as many as keep several CTAs' heaps (12 bytes per entry) resident

@@ -282,6 +282,33 @@ def test_grid_knn_equals_brute_force_bit_for_bit(d, layout):
     assert torch.equal(g1, b1)
 
 
+@pytest.mark.parametrize("k", [5, 50, 64, 65, 100, 128, 129])
+def test_grid_knn_kernel_selection_and_overflow(k):
+    """The warp-per-query grid kernel (k <= 128: candidate list of 256 entries up to k = 64, 512
+    above, exact radix selection, serial fallback when the list overflows or one distance is
+    shared by more than 32 rows) and the thread-per-query kernel (k > 128) against brute force,
+    bit for bit: uniform data with one cell holding thousands of points (overflow), a block of
+    exact duplicates (ties at distance 0) and queries on both."""
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(900 + k)
+    n = 30_000
+    x = rng.uniform(size=(n, 2))
+    x[:4000] = 0.5 + 1e-4 * rng.normal(size=(4000, 2))   # one very dense cell
+    x[4000:4100] = np.array([0.25, 0.75])                # 100 copies of one point
+    q = np.concatenate([rng.uniform(size=(1500, 2)), 0.5 + 2e-4 * rng.normal(size=(300, 2)),
+                        np.tile([[0.25, 0.75]], (10, 1)), x[:200]])
+    xd, qd = dev(x), dev(q)
+    grid = ops.KnnGrid(xd)
+    gi, gd = grid.query(qd, k)
+    bi, bd = ops.knn(xd, qd, k)
+    assert torch.equal(gi, bi) and torch.equal(gd, bd)
+    rows = dev(np.arange(3900, 4150))
+    gi2, gd2 = grid.query(xd[rows], k, self_idx=rows)
+    bi2, bd2 = ops.knn(xd, xd[rows], k, self_idx=rows)
+    assert torch.equal(gi2, bi2) and torch.equal(gd2, bd2)
+
+
 def test_fast_coefficients_reproducible_over_many_launches(ops):
     """Regression: stale NaNs in never-assembled shared-memory cells once leaked into the
     coefficient back substitution on some launches.  Interleave other launches (which leave
