@@ -543,8 +543,17 @@ def run_ours(args):
     bnn, _ = nbrs.get_batch_nns(bi)
     loo = {}
     n_eval = 40
+    loo_collective = "none (1 GPU)"
     for lname, lfn in (("mse", mse_fn), ("lool", lool_fn)):
         obj = make_fused_loo_crossval_fn(model, lfn, bi, bnn, x, y, distributed=world > 1)
+        if world > 1:
+            # what the evaluations actually use: the one-shot NVLink peer-memory sum in the
+            # objective kernel's epilogue when symmetric memory is available, else NCCL
+            from muygpys_b200.distributed import PartialsReducer
+            fused_peers = PartialsReducer(x.device).peers is not None
+            loo_collective = ("SUM of the 8-double record over NVLink peer memory inside the "
+                              "objective kernel (mgp_fused_loo_peers)" if fused_peers else
+                              "1 NCCL SUM all-reduce of 8 doubles per eval")
         for _ in range(5):
             obj(length_scale=0.1)
         barrier()
@@ -854,8 +863,7 @@ def run_ours(args):
                     "neighbourhoods_per_s": loo["mse"]["neighbourhoods_per_s"],
                     "mse": loo["mse"], "lool": loo["lool"],
                     "cpu_baseline": cpu_loo,
-                    "collective": "1 NCCL SUM all-reduce of 8 doubles per eval" if world > 1
-                                  else "none (1 GPU)"},
+                    "collective": loo_collective},
             "configs": configs,
         }
         print(json.dumps(out))

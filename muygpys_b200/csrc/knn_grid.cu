@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) knn_grid_warp_kernel(const Grid
     const int n1 = hi1 - lo1 + 1, rows = n1 * (hi2 - lo2 + 1);
     long long cnt = 0;
     for (int i = lane; i < rows; i += 32) {
-      const int cz = lo2 + i / n1, cy = lo1 + i % n1;
+      const int cz = (D > 2) ? lo2 + i / n1 : 0, cy = (D > 2) ? lo1 + i % n1 : lo1 + i;
       const long long base = ((long long)cz * g.dims[1] + cy) * g.dims[0];
       cnt += g.cell_start[base + hi0 + 1] - g.cell_start[base + lo0];
     }
@@ -531,8 +531,56 @@ __global__ void __launch_bounds__(GW_WARPS * 32) knn_grid_warp_kernel(const Grid
     return;
   }
   __syncwarp();
+  if (count <= 64) {
+    // The list holds the answer: order it by (distance, row) in REGISTERS -- entries e = lane
+    // and e = lane + 32, a 64-element bitonic network whose only intra-lane step is stride 32
+    // (half the instructions of the shared-memory network below, no barriers).
+    double d0 = lane < count ? sd[lane] : DBL_MAX, d1 = lane + 32 < count ? sd[lane + 32] : DBL_MAX;
+    int i0 = lane < count ? si[lane] : INT_MAX, i1 = lane + 32 < count ? si[lane + 32] : INT_MAX;
+    auto cross = [&](double& d, int& i, int stride, bool up) {
+      const double od = __shfl_xor_sync(0xffffffffu, d, stride);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, stride);
+      const bool lower = (lane & stride) == 0;
+      if (key_less(od, oi, d, i) == (lower == up)) {
+        d = od;
+        i = oi;
+      }
+    };
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        // row 0 (e < 32) sorts ascending, row 1 descending at size 32: a bitonic sequence of 64
+        const bool up0 = (lane & size) == 0;
+        cross(d0, i0, stride, size == 32 ? true : up0);
+        cross(d1, i1, stride, size == 32 ? false : up0);
+      }
+    }
+    if (key_less(d1, i1, d0, i0)) {  // stride 32
+      const double td = d0;
+      const int ti = i0;
+      d0 = d1;
+      i0 = i1;
+      d1 = td;
+      i1 = ti;
+    }
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+      cross(d0, i0, stride, true);
+      cross(d1, i1, stride, true);
+    }
+    if (lane < k) {
+      g.out_idx[qi * k + lane] = lane < count ? i0 : INT_MAX;
+      g.out_d2[qi * k + lane] = lane < count ? d0 : DBL_MAX;
+    }
+    if (lane + 32 < k) {
+      g.out_idx[qi * k + lane + 32] = lane + 32 < count ? i1 : INT_MAX;
+      g.out_d2[qi * k + lane + 32] = lane + 32 < count ? d1 : DBL_MAX;
+    }
+    return;
+  }
   {
-    // the list holds the answer; order it by (distance, row)
+    // (k > 64) the same through shared memory
     int P = 2;
     while (P < count) P <<= 1;
     for (int i = count + lane; i < P; i += 32) {
