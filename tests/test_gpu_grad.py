@@ -115,3 +115,50 @@ def test_lbfgsb_with_gradient_reaches_the_finite_difference_optimum():
     gr_opt = optimize_from_indices(model, bi, bnn, x, y, loss_fn=lool_fn, use_gradient=True)
     a, b = fd_opt.get_opt_params()[1], gr_opt.get_opt_params()[1]
     np.testing.assert_allclose(b, a, rtol=2e-3)
+
+
+@pytest.mark.parametrize("d,k,kid", [(2, 50, 2), (1, 7, 1), (3, 23, 3), (2, 47, 4), (2, 62, 1),
+                                     (3, 38, 2)])
+def test_back_substitution_kernels_agree(d, k, kid):
+    """The two independent implementations of the back substitution -- the thread-per-tile
+    kernel's GRAD instantiation (variant 0, csrc/fused_tp.cuh: factor warp, one slot per tile)
+    and the lane-parallel column kernel (variant 4, csrc/fused_col.cuh) -- on the same inputs:
+    loss / scale partials, the 20 gradient sums and the fast-mean coefficients agree to
+    rounding (the factorisations are bit-identical, the summation orders differ), and repeated
+    launches are bit-reproducible."""
+    from muygpys_b200 import _lib as L
+    from muygpys_b200 import ops
+
+    rng = np.random.default_rng(7000 + 10 * k + d)
+    n, b = 6000, 1531  # (not a multiple of any kernel's neighbourhoods per CTA)
+    x = dev_t(rng.uniform(size=(n, d)))
+    y = dev_t(np.sin(3 * rng.uniform(size=n)) + 0.1 * rng.normal(size=n))
+    bi = dev_t(np.sort(rng.choice(n, b, replace=False)))
+    nn, _ = ops.knn(x, x[bi], k + 1)
+    nn = nn[:, 1:].contiguous()
+    mid = 1 if kid == 0 else 0
+    ls = [0.2, 0.35, 0.5][:d] if k % 2 else 0.3
+    got = {}
+    try:
+        for variant in (0, 4):
+            ops.set_fused_variant(variant)
+            loo = ops.FusedLoo(x, y, bi, nn, kernel_id=kid, metric_id=mid, loss_id=L.LOSS_LOOL,
+                               want_grad=True)
+            rec = loo.record(loo.launch(ls, 1e-3)).copy()
+            grad = loo.grad.numpy().copy()
+            again = loo.record(loo.launch(ls, 1e-3))
+            np.testing.assert_array_equal(again, rec)
+            np.testing.assert_array_equal(loo.grad.numpy(), grad)
+            co = ops.fused_posterior(x, x, bi, nn, y, kernel_id=kid, metric_id=mid,
+                                     length_scale=ls, noise=1e-3, want_coeffs=True)
+            got[variant] = (rec, grad, co["coeffs"].cpu().numpy(), co["mean"].cpu().numpy())
+    finally:
+        ops.set_fused_variant(0)
+    for a, b_, name in zip(got[0], got[4], ("partials", "gradient sums", "coefficients", "mean")):
+        scale = np.max(np.abs(b_)) + 1e-300
+        assert np.max(np.abs(a - b_)) <= 1e-10 * scale, (name, np.max(np.abs(a - b_)) / scale)
+    assert np.all(np.isfinite(got[0][2]))
+
+
+def dev_t(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
