@@ -607,42 +607,46 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       if (GRAD)  // Xout is column-major (B-fragment order): M[rho][2q], M[rho][2q+1]
         *reinterpret_cast<double2*>(Ms + J * 64 + 2 * lane) =
             make_double2(Xout[16 * q + rho], Xout[16 * q + 8 + rho]);
-      double n0[T], n1[T];
-      double2 raw[T];
-#pragma unroll
-      for (int I = J + 1; I < T; ++I)
-        raw[I] = *reinterpret_cast<const double2*>(Ls + slot_off(I, J) + 2 * lane);
+      // tile row J + 1: finished tile, then the next diagonal tile
+      double m0 = 0.0, m1 = 0.0;
       {
-        const int I = J + 1;
-        n0[I] = 0.0;
-        n1[I] = 0.0;
-        dmma_free(n0[I], n1[I], raw[I].x, bm.x);
-        dmma_free(n0[I], n1[I], raw[I].y, bm.y);
+        const double2 raw = *reinterpret_cast<const double2*>(Ls + slot_off(J + 1, J) + 2 * lane);
+        dmma_free(m0, m1, raw.x, bm.x);
+        dmma_free(m0, m1, raw.y, bm.y);
       }
-      const double bj0 = n0[J + 1] * nd.x, bj1 = n1[J + 1] * nd.y;
-      dmma_free(c[J + 1][0], c[J + 1][1], n0[J + 1], bj0);
-      dmma_free(c[J + 1][0], c[J + 1][1], n1[J + 1], bj1);
+      const double bj0 = m0 * nd.x, bj1 = m1 * nd.y;
+      dmma_free(c[J + 1][0], c[J + 1][1], m0, bj0);
+      dmma_free(c[J + 1][0], c[J + 1][1], m1, bj1);
       if (J + 1 < T - 1) hand_off(J + 1);
       TP_TRACE(warp, 32 + J);
-      *reinterpret_cast<double2*>(Ls + slot_off(J + 1, J) + 2 * lane) =
-          make_double2(n0[J + 1], n1[J + 1]);
+      *reinterpret_cast<double2*>(Ls + slot_off(J + 1, J) + 2 * lane) = make_double2(m0, m1);
+      if (J == T - 2 && kl == 7) out_mean = -shfl_d(m1, 3);
+      // the other rows, two at a time (few live registers: the raw tiles of column J + 1 wait in
+      // c[][] meanwhile): U = S M, stored; column J's term subtracted from column J + 1; that
+      // tile parked raw in the slot its finished version will take
 #pragma unroll
-      for (int I = J + 2; I < T; ++I) {
-        n0[I] = 0.0;
-        n1[I] = 0.0;
-        dmma_free(n0[I], n1[I], raw[I].x, bm.x);
+      for (int Ia = J + 2; Ia < T; Ia += 2) {
+        const int Ib = (Ia + 1 < T) ? Ia + 1 : Ia;
+        const double2 ra = *reinterpret_cast<const double2*>(Ls + slot_off(Ia, J) + 2 * lane);
+        const double2 rb = *reinterpret_cast<const double2*>(Ls + slot_off(Ib, J) + 2 * lane);
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        dmma_free(a0, a1, ra.x, bm.x);
+        if (Ib != Ia) dmma_free(b0, b1, rb.x, bm.x);
+        dmma_free(a0, a1, ra.y, bm.y);
+        if (Ib != Ia) dmma_free(b0, b1, rb.y, bm.y);
+        *reinterpret_cast<double2*>(Ls + slot_off(Ia, J) + 2 * lane) = make_double2(a0, a1);
+        if (Ib != Ia)
+          *reinterpret_cast<double2*>(Ls + slot_off(Ib, J) + 2 * lane) = make_double2(b0, b1);
+        dmma_free(c[Ia][0], c[Ia][1], a0, bj0);
+        if (Ib != Ia) dmma_free(c[Ib][0], c[Ib][1], b0, bj0);
+        dmma_free(c[Ia][0], c[Ia][1], a1, bj1);
+        if (Ib != Ia) dmma_free(c[Ib][0], c[Ib][1], b1, bj1);
+        *reinterpret_cast<double2*>(Ls + slot_off(Ia, J + 1) + 2 * lane) =
+            make_double2(c[Ia][0], c[Ia][1]);
+        if (Ib != Ia)
+          *reinterpret_cast<double2*>(Ls + slot_off(Ib, J + 1) + 2 * lane) =
+              make_double2(c[Ib][0], c[Ib][1]);
       }
-#pragma unroll
-      for (int I = J + 2; I < T; ++I) {
-        dmma_free(n0[I], n1[I], raw[I].y, bm.y);
-        *reinterpret_cast<double2*>(Ls + slot_off(I, J) + 2 * lane) = make_double2(n0[I], n1[I]);
-      }
-      if (J == T - 2 && kl == 7) out_mean = -shfl_d(n1[T - 1], 3);
-#pragma unroll
-      for (int I = J + 2; I < T; ++I) dmma_free(c[I][0], c[I][1], n0[I], bj0);
-#pragma unroll
-      for (int I = J + 2; I < T; ++I) dmma_free(c[I][0], c[I][1], n1[I], bj1);
-      park_below(J + 1);
     };
 
     // ---- preparation of a neighbourhood, in pieces that need nothing from the factor warp.
