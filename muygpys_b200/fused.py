@@ -58,9 +58,13 @@ def _fused_pipelined(spec: ModelSpec, indices, nn_indices, test_features, train_
         x, q_dev, indices, nn_indices, y, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
         length_scale=spec.length_scale_arg(), noise=spec.noise(None), scale=spec.scale(),
         want_mean=want_mean, want_var=want_var)
-    # the staged host index tensors must outlive the asynchronous uploads
-    torch.cuda.current_stream().synchronize()
-    return {"mean": out.get("mean"), "var": out.get("var")}
+    # No host synchronisation here: the pipeline is joined back into the current stream, so
+    # whatever the caller enqueues next (a device-to-host copy of the results, the next batch)
+    # is ordered behind it, and the host is free to prepare the next call meanwhile.  The staged
+    # HOST tensors must outlive the asynchronous uploads: fused_regress ties them to the result
+    # tensors it returns (whoever reads the results synchronises first).
+    return {"mean": out.get("mean"), "var": out.get("var"),
+            "_keepalive": out.get("_host_buffers")}
 
 
 def _squeeze_response(mean: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
@@ -87,6 +91,11 @@ def fused_regress(muygps, indices, nn_indices, test_features, train_features, tr
         res.append(like_input(_squeeze_response(out["mean"], fdev(train_targets)), *host))
     if want_var:
         res.append(like_input(out["var"], *host))
+    keep = out.get("_keepalive")
+    if keep is not None:
+        for t in res:
+            if isinstance(t, torch.Tensor):  # (numpy results were copied out: already synced)
+                t._mgp_keepalive = keep
     return tuple(res) if len(res) > 1 else res[0]
 
 
