@@ -144,7 +144,7 @@ int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_idx_host,
 /* Test/bench hook: 0 = choose automatically (thread-per-tile > tile > generic), 1 = always the
  * generic shared-memory kernel, 2 = the register-tile DMMA kernel where supported, 3 = the
  * thread-per-tile kernel (error if the shape is unsupported: r == 1, d <= 3, homoscedastic
- * nugget, 7 <= k <= 102; <= 62 with coefficients), 4 = its lane-parallel predecessor, the
+ * nugget, 7 <= k <= 102, with or without coefficients), 4 = its lane-parallel predecessor, the
  * column-direct kernel (k <= 62).  Lets the independently written variants be cross-checked on
  * identical inputs. */
 int mgp_set_fused_variant(int32_t variant);
@@ -206,7 +206,7 @@ int mgp_fused_loo_peers(const mgp_problem* p, int32_t loss_id, double boundary_s
  *   grad[5t+4] = sum d yky                                   -> d sigma^2 (analytic scale)
  * from which the host finishes d mse and d lool (muygpys_b200/objective.py).  grad == NULL is
  * mgp_fused_loo_peers.  The gradient sums are per rank: `partials` goes through the peer
- * exchange, `grad` is summed across ranks by the caller.  With grad != NULL: k <= 62. */
+ * exchange, `grad` is summed across ranks by the caller.  grad != NULL takes the same shapes (k <= 102). */
 int mgp_fused_loo_grad(const mgp_problem* p, int32_t loss_id, double boundary_scale,
                        double* partials, double* grad, void* ws, size_t ws_bytes,
                        const mgp_peer_group* g, void* stream);

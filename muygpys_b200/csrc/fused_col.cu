@@ -22,11 +22,11 @@ MGP_TP_ALL_T(MGP_TP_DECL, 1)
 MGP_TP_ALL_T(MGP_TP_DECL, 2)
 MGP_TP_ALL_T(MGP_TP_DECL, 3)
 #undef MGP_TP_DECL
-// ... and with the back substitution / gradient epilogue (T <= 8)
+// ... and with the back substitution / gradient epilogue (GRAD instantiations, every T)
 #define MGP_TPG_DECL(F, T)                                                                  \
   int launch_fused_tpg_f##F##_t##T(const mgp_problem*, const Model&, const ColLoo&, int*, \
                                    cudaStream_t);
-#define MGP_TPG_ALL_T(X, F) X(F, 2) X(F, 3) X(F, 4) X(F, 5) X(F, 6) X(F, 7) X(F, 8)
+#define MGP_TPG_ALL_T(X, F) MGP_TP_ALL_T(X, F)
 MGP_TPG_ALL_T(MGP_TPG_DECL, 0)
 MGP_TPG_ALL_T(MGP_TPG_DECL, 1)
 MGP_TPG_ALL_T(MGP_TPG_DECL, 2)
@@ -55,8 +55,9 @@ static int col_formula(const Model& model) {
 
 // Shapes the column-direct kernels take: r = 1, d <= 3, homoscedastic nugget, the four closed
 // covariance formulas; k = 7..102 (T = 2..13 tile rows) for plain prediction and the one-launch
-// objective (thread-per-tile kernel), k <= 62 (T <= 8) where the back substitution is needed
-// (fast-mean coefficients, analytic gradient: GRAD instantiations of fused_col_kernel).
+// objective and for the back substitution (fast-mean coefficients, analytic gradient: GRAD
+// instantiations of the thread-per-tile kernel); the lane-parallel column kernel (variant 4)
+// stops at k = 62 (T <= 8).
 static int col_shape_ok(const mgp_problem* p, const Model& model, int max_tiles) {
   if (p->r != 1 || p->d > 3 || p->noise_bk || !p->train_y) return 0;
   const int T = col_tiles(p->k);
@@ -68,7 +69,7 @@ static int col_shape_ok(const mgp_problem* p, const Model& model, int max_tiles)
 }
 
 int fused_col_supported(const mgp_problem* p, const Model& model) {
-  return col_shape_ok(p, model, p->coeffs ? COL_MAX_T : TP_MAX_T);
+  return col_shape_ok(p, model, TP_MAX_T);
 }
 
 static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& loo, int* grid_out,
@@ -79,10 +80,6 @@ static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& lo
   MGP_REQUIRE(f >= 0 && f < 4 && T >= 2 && T <= TP_MAX_T, MGP_ERR_UNSUPPORTED,
               "column kernels do not support this kernel / metric pair or k = %d", p->k);
   const bool backsub = loo.grad != nullptr || loo.backsub;
-  if (backsub)
-    MGP_REQUIRE(T <= COL_MAX_T, MGP_ERR_UNSUPPORTED,
-                "coefficients / analytic gradient: k = %d needs more than %d tile rows", p->k,
-                COL_MAX_T);
   // Variant 4 (cross-check of the thread-per-tile kernels): the lane-parallel column kernel,
   // GRAD instantiation -- its back substitution goes unused for a plain prediction.
   if (fused_variant() == 4 && T <= COL_MAX_T) {
@@ -95,7 +92,7 @@ static int launch_col(const mgp_problem* p, const Model& model, const ColLoo& lo
   }
   if (backsub) {
 #define MGP_TPG_ENTRY(F, TT) launch_fused_tpg_f##F##_t##TT,
-    static const launcher gtable[4][COL_MAX_T - 1] = {{MGP_TPG_ALL_T(MGP_TPG_ENTRY, 0)},
+    static const launcher gtable[4][TP_MAX_T - 1] = {{MGP_TPG_ALL_T(MGP_TPG_ENTRY, 0)},
                                                       {MGP_TPG_ALL_T(MGP_TPG_ENTRY, 1)},
                                                       {MGP_TPG_ALL_T(MGP_TPG_ENTRY, 2)},
                                                       {MGP_TPG_ALL_T(MGP_TPG_ENTRY, 3)}};
@@ -215,7 +212,7 @@ extern "C" int mgp_fused_loo_grad(const mgp_problem* p, int32_t loss_id, double 
   rc = make_model(p->kernel_id, p->metric_id, p->d, p->length_scale_count, p->length_scale,
                   &model);
   if (rc != MGP_OK) return rc;
-  MGP_REQUIRE(col_shape_ok(p, model, grad ? COL_MAX_T : TP_MAX_T), MGP_ERR_UNSUPPORTED,
+  MGP_REQUIRE(col_shape_ok(p, model, TP_MAX_T), MGP_ERR_UNSUPPORTED,
               "mgp_fused_loo: shape not supported by the column kernels (k=%d d=%d r=%d%s)", p->k,
               p->d, p->r, grad ? ", analytic gradient" : "");
   MGP_REQUIRE(p->query_x == p->train_x && p->query_idx != nullptr, MGP_ERR_BAD_ARG,

@@ -860,19 +860,23 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
       for (int f = 0; f < D; ++f) Gmc[f] = Gvc[f] = 0.0;
       {
         const Pt<D> pq = ld_pt<D>(pts, k);
-        const int ja = min(lane, k), jb = min(lane + 32, k);
-        const Pt<D> p0 = ld_pt<D>(pts, ja), p1 = ld_pt<D>(pts, jb);
-        const double u[2] = {sq_dist<D>(pq, p0), sq_dist<D>(pq, p1)};
-        double ph[2];
-        cov_n<F, 2, 1>(u, tab64, ph);
-        const double w0 = lane < k ? wv[ja] : 0.0, a0 = lane < k ? av[ja] : 0.0;
-        const double w1 = lane + 32 < k ? wv[jb] : 0.0, a1 = lane + 32 < k ? av[jb] : 0.0;
 #pragma unroll
-        for (int f = 0; f < D; ++f) {
-          const double d0 = pq.x[f] - p0.x[f], d1 = pq.x[f] - p1.x[f];
-          const double g0 = ph[0] * (d0 * d0), g1 = ph[1] * (d1 * d1);
-          Gmc[f] = fma(g0, a0, fma(g1, a1, Gmc[f]));
-          Gvc[f] = fma(g0, w0, fma(g1, w1, Gvc[f]));
+        for (int c0 = 0; c0 < 8 * T; c0 += 64) {  // 64 entries of the row per pass
+          const int ia = c0 + lane, ib = c0 + lane + 32;
+          const int ja = min(ia, k), jb = min(ib, k);
+          const Pt<D> p0 = ld_pt<D>(pts, ja), p1 = ld_pt<D>(pts, jb);
+          const double u[2] = {sq_dist<D>(pq, p0), sq_dist<D>(pq, p1)};
+          double ph[2];
+          cov_n<F, 2, 1>(u, tab64, ph);
+          const double w0 = ia < k ? wv[ja] : 0.0, a0 = ia < k ? av[ja] : 0.0;
+          const double w1 = ib < k ? wv[jb] : 0.0, a1 = ib < k ? av[jb] : 0.0;
+#pragma unroll
+          for (int f = 0; f < D; ++f) {
+            const double d0 = pq.x[f] - p0.x[f], d1 = pq.x[f] - p1.x[f];
+            const double g0 = ph[0] * (d0 * d0), g1 = ph[1] * (d1 * d1);
+            Gmc[f] = fma(g0, a0, fma(g1, a1, Gmc[f]));
+            Gvc[f] = fma(g0, w0, fma(g1, w1, Gvc[f]));
+          }
         }
       }
       // nugget: dK = I

@@ -347,9 +347,9 @@ class FusedLoo:
 def fused_loo_supported(d: int, k: int, r: int, kernel_id: int, metric_id: int,
                         heteroscedastic: bool, grad: bool = False) -> bool:
     """Shapes `mgp_fused_loo` / `mgp_fused_loo_grad` take (mirrors col_shape_ok in
-    csrc/fused_col.cu): k = 7..102 for the objective (thread-per-tile kernel, up to 13 tile rows),
-    k <= 62 with the analytic gradient (back substitution in the column kernel, 8 tile rows)."""
-    if r != 1 or d > 3 or heteroscedastic or not 7 <= k <= (62 if grad else 102):
+    csrc/fused_col.cu): k = 7..102 (thread-per-tile kernel, up to 13 tile rows), with or without
+    the analytic gradient (GRAD instantiations: back substitution on the stored factor)."""
+    if r != 1 or d > 3 or heteroscedastic or not 7 <= k <= 102:
         return False
     if metric_id == L.METRIC_L2:
         return kernel_id in (L.KERNEL_MATERN_05, L.KERNEL_MATERN_15, L.KERNEL_MATERN_25,

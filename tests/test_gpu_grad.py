@@ -51,6 +51,12 @@ CASES = [
     ("rbf", 0.2, 1, 30, "mse", False, True),
     (np.inf, 0.4, 2, 47, "lool", True, False),   # k % 8 == 7: augmented rows straddle tiles
     (1.5, 0.25, 2, 62, "lool", False, True),
+    # k > 62: GRAD instantiations with 9..13 tile rows (C4 is the k = 100 case)
+    (2.5, [0.3, 0.6], 2, 100, "lool", True, False),
+    (1.5, 0.3, 2, 63, "mse", False, True),
+    (0.5, [0.4, 0.3, 0.5], 3, 79, "lool", False, True),
+    ("rbf", 0.2, 1, 88, "mse", False, True),
+    (np.inf, 0.4, 2, 102, "lool", True, False),
 ]
 
 
@@ -103,6 +109,32 @@ def test_gradient_against_oracle_objective():
     h = 1e-5 * ls
     fd = (oracle(ls + h) - oracle(ls - h)) / (2 * h)
     assert abs(grads["length_scale"] - fd) <= 1e-6 * abs(fd), (grads, fd)
+
+
+def test_gradient_against_oracle_objective_c4_shape():
+    """The C4 shape (anisotropic Matern 5/2, k = 100, lool with the analytic scale): both length
+    scales against central differences of the oracle's objective (isotropic oracle calls are not
+    enough here, so the deformation is rebuilt per evaluation)."""
+    from muygpys_b200.optimize.loss import lool_fn
+    from muygpys_b200.optimize.objective import make_fused_loo_value_and_grad_fn
+
+    x, y, bi, bnn = _setup(11, 2500, 120, 2, 100)
+    model = _model(2.5, [0.1, 0.5], 1e-3, True)
+    vg = make_fused_loo_value_and_grad_fn(model, lool_fn, bi, bnn, x, y)
+    ls = np.array([0.12, 0.45])
+    val, grads = vg(length_scale0=ls[0], length_scale1=ls[1])
+
+    def oracle(l):
+        return O.loo_objective(O.LOSS_LOOL, O.KERNEL_MATERN_25, O.METRIC_L2, np.asarray(l), 1e-3,
+                               x, y, bi, bnn)[0]
+
+    assert abs(val - oracle(ls)) <= 1e-10 * abs(val)
+    for f in range(2):
+        h = 1e-5 * ls[f]
+        e = np.zeros(2)
+        e[f] = h
+        fd = (oracle(ls + e) - oracle(ls - e)) / (2 * h)
+        assert abs(grads[f"length_scale{f}"] - fd) <= 1e-6 * abs(fd), (f, grads, fd)
 
 
 def test_lbfgsb_with_gradient_reaches_the_finite_difference_optimum():

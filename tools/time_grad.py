@@ -15,7 +15,7 @@ from muygpys_b200.optimize.loss import lool_fn, mse_fn
 from muygpys_b200.optimize.objective import make_fused_loo_crossval_fn, make_fused_loo_value_and_grad_fn
 
 rng = np.random.default_rng(4)
-n, b, k = 1_000_000, 10_000, 50
+n, b, k = int(os.environ.get("N", 1_000_000)), 10_000, int(os.environ.get("K", 50))
 x = torch.as_tensor(rng.uniform(size=(n, 2))).cuda()
 xn = x.cpu().numpy()
 y = torch.as_tensor(np.sin(4 * xn[:, 0]) + np.cos(3 * xn[:, 1]) + 0.3 * np.sin(11 * xn[:, 0] * xn[:, 1]) + 0.05 * rng.normal(size=n)).cuda()
