@@ -694,6 +694,19 @@ def run_ours(args):
             obj4(length_scale0=0.08 + 0.002 * i, length_scale1=0.5)
         barrier()
         secs4 = allmax(time.perf_counter() - t0)
+        # analytic gradient (both length scales) in one launch, against the 1 + p = 3 plain
+        # evaluations the reference's finite differences need
+        from muygpys_b200.optimize.objective import make_fused_loo_value_and_grad_fn
+        vg4 = make_fused_loo_value_and_grad_fn(model4, lool_fn, bi4, bnn4, x4, y4,
+                                               distributed=world > 1)
+        for _ in range(3):
+            vg4(length_scale0=0.1, length_scale1=0.5)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n4e):
+            vg4(length_scale0=0.08 + 0.002 * i, length_scale1=0.5)
+        barrier()
+        secs4g = allmax(time.perf_counter() - t0)
         kw4 = dict(kernel_id=KERNEL_M25, metric_id=METRIC_L2, length_scale=[0.1, 0.5], noise=NOISE,
                    want_yky=True)
         ms4 = timed_ms(lambda: ops.fused_posterior(x4, x4, bi4, bnn4, y4, **kw4), 10)
@@ -703,6 +716,8 @@ def run_ours(args):
                "rows_per_gpu": b4, "ms": ms4, "value": world * b4 / (ms4 * 1e-3),
                "unit": "neighbourhoods/s (fused kernel: mean, variance, y^T K^-1 y)",
                "loo_evals_per_s": n4e / secs4, "loo_us_per_eval": 1e6 * secs4 / n4e,
+               "loo_value_and_grad_us_per_eval": 1e6 * secs4g / n4e,
+               "loo_finite_difference_us_per_gradient": 3e6 * secs4 / n4e,
                "knn_ms": knn4, "knn_index_build_s": knn4_build,
                "roofline": roof_fp64(b4 / (ms4 * 1e-3), f4)}
         if not skip_cpu:
@@ -719,7 +734,7 @@ def run_ours(args):
                 c["scaled_to_10k_rows_evals_per_s"] = c["evals_per_s"] * rows4 / b4
                 rec["cpu_baseline"] = c
         configs["C4"] = rec
-        del x4, y4, nb4, bnn4, obj4
+        del x4, y4, nb4, bnn4, obj4, vg4
         torch.cuda.empty_cache()
 
         # -- C5: scale-out posterior, 100M train / 10M test, Matern 1/2, k = 50 ----------------
