@@ -141,6 +141,16 @@ int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_idx_host,
                              const int64_t* query_idx_host, double* mean_host,
                              double* var_host, void* ws, size_t ws_bytes, void* stream);
 
+/* The same call for a caller that holds its neighbour indices as 32-bit integers (numpy
+ * accepts any integer dtype as an index array, S/_src/gp/tensors/numpy.py:47-94): half the
+ * bytes cross the host link -- the C2 step uploads 21.6 MB instead of 42.4 MB.  `nn_stage32`
+ * is a DEVICE buffer of b*k int32 the chunks land in; a small kernel widens each chunk into
+ * p->nn_idx (int64, what every kernel reads) ahead of the chunk's fused launch. */
+int mgp_fused_posterior_host32(const mgp_problem* p, const int32_t* nn_idx_host32,
+                               int32_t* nn_stage32, const int64_t* query_idx_host,
+                               double* mean_host, double* var_host, void* ws, size_t ws_bytes,
+                               void* stream);
+
 /* Test/bench hook: 0 = choose automatically (thread-per-tile > tile > generic), 1 = always the
  * generic shared-memory kernel, 2 = the register-tile DMMA kernel where supported, 3 = the
  * thread-per-tile kernel (error if the shape is unsupported: r == 1, d <= 3, homoscedastic

@@ -70,6 +70,7 @@ SIGNATURES = {
     "mgp_fused_workspace_bytes": (_sz, [_PP]),
     "mgp_fused_posterior": (C.c_int, [_PP, _dp, _sz, _dp]),
     "mgp_fused_posterior_host": (C.c_int, [_PP, _dp, _dp, _dp, _dp, _dp, _sz, _dp]),
+    "mgp_fused_posterior_host32": (C.c_int, [_PP, _dp, _dp, _dp, _dp, _dp, _dp, _sz, _dp]),
     "mgp_set_fused_variant": (C.c_int, [_i32]),
     "mgp_fused_loo_workspace_bytes": (_sz, [_PP]),
     "mgp_fused_loo": (C.c_int, [_PP, _i32, _f64, _dp, _dp, _sz, _dp]),

@@ -90,6 +90,26 @@ std::vector<long long> chunk_bounds(long long b, long long wave) {
   return bounds;
 }
 
+// 32-bit neighbour indices (half the bytes on the host link) widened on the device into the
+// int64 staging buffer the kernels read: four per thread where both sides are 16-byte aligned.
+__global__ void __launch_bounds__(256) widen_idx_kernel(const int32_t* __restrict__ src,
+                                                        int64_t* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)dst) & 15) == 0) {
+    const long long n4 = n >> 2;
+    for (long long v = i; v < n4; v += stride) {
+      const int4 a = reinterpret_cast<const int4*>(src)[v];
+      longlong2* o = reinterpret_cast<longlong2*>(dst) + 2 * v;
+      o[0] = make_longlong2(a.x, a.y);
+      o[1] = make_longlong2(a.z, a.w);
+    }
+    for (long long e = (n4 << 2) + i; e < n; e += stride) dst[e] = src[e];
+  } else {
+    for (; i < n; i += stride) dst[i] = src[i];
+  }
+}
+
 }  // namespace
 
 int validate_problem(const mgp_problem* p);
@@ -99,13 +119,16 @@ int fused_wave_per_sm(const mgp_problem* p);
 
 using namespace mgp;
 
-extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_idx_host,
-                                        const int64_t* query_idx_host, double* mean_host,
-                                        double* var_host, void* ws, size_t ws_bytes,
-                                        void* stream) {
+static int fused_posterior_host_impl(const mgp_problem* p, const int64_t* nn_idx_host,
+                                     const int32_t* nn_idx_host32, int32_t* nn_stage32,
+                                     const int64_t* query_idx_host, double* mean_host,
+                                     double* var_host, void* ws, size_t ws_bytes, void* stream) {
   MGP_REQUIRE(p != nullptr, MGP_ERR_BAD_ARG, "null problem");
-  MGP_REQUIRE(nn_idx_host != nullptr && p->nn_idx != nullptr, MGP_ERR_BAD_ARG,
+  MGP_REQUIRE((nn_idx_host != nullptr || nn_idx_host32 != nullptr) && p->nn_idx != nullptr,
+              MGP_ERR_BAD_ARG,
               "nn_idx_host and the device staging buffer p->nn_idx are required");
+  MGP_REQUIRE(nn_idx_host32 == nullptr || nn_stage32 != nullptr, MGP_ERR_BAD_ARG,
+              "32-bit host indices need the int32 device staging buffer");
   MGP_REQUIRE(!query_idx_host || p->query_idx, MGP_ERR_BAD_ARG,
               "query_idx_host needs the device staging buffer p->query_idx");
   MGP_REQUIRE(!mean_host || p->mean, MGP_ERR_BAD_ARG, "mean_host needs the device buffer p->mean");
@@ -160,13 +183,24 @@ extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_
     if (rows <= 0) continue;
     cudaEvent_t uploaded = ss->chunk_ev[2 * c], computed = ss->chunk_ev[2 * c + 1];
     int64_t* nn_dev = const_cast<int64_t*>(p->nn_idx) + lo * k;
-    MGP_CUDA(cudaMemcpyAsync(nn_dev, nn_idx_host + lo * k, (size_t)rows * k * sizeof(int64_t),
-                             cudaMemcpyHostToDevice, up));
+    if (nn_idx_host32)
+      MGP_CUDA(cudaMemcpyAsync(nn_stage32 + lo * k, nn_idx_host32 + lo * k,
+                               (size_t)rows * k * sizeof(int32_t), cudaMemcpyHostToDevice, up));
+    else
+      MGP_CUDA(cudaMemcpyAsync(nn_dev, nn_idx_host + lo * k, (size_t)rows * k * sizeof(int64_t),
+                               cudaMemcpyHostToDevice, up));
     if (query_idx_host)
       MGP_CUDA(cudaMemcpyAsync(const_cast<int64_t*>(p->query_idx) + lo, query_idx_host + lo,
                                (size_t)rows * sizeof(int64_t), cudaMemcpyHostToDevice, up));
     MGP_CUDA(cudaEventRecord(uploaded, up));
     MGP_CUDA(cudaStreamWaitEvent(run, uploaded, 0));
+    if (nn_idx_host32) {
+      const long long cnt = rows * k;
+      const long long want = (cnt / 4 + 255) / 256;
+      const int blocks = (int)(want < 1 ? 1 : want > 4LL * sm_count() ? 4LL * sm_count() : want);
+      widen_idx_kernel<<<blocks, 256, 0, run>>>(nn_stage32 + lo * k, nn_dev, cnt);
+      MGP_CUDA(cudaGetLastError());
+    }
     mgp_problem sub = *p;
     sub.b = rows;
     sub.nn_idx = nn_dev;
@@ -206,4 +240,22 @@ extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_
   }
 #undef MGP_CUDA
   return MGP_OK;
+}
+
+extern "C" int mgp_fused_posterior_host(const mgp_problem* p, const int64_t* nn_idx_host,
+                                        const int64_t* query_idx_host, double* mean_host,
+                                        double* var_host, void* ws, size_t ws_bytes,
+                                        void* stream) {
+  MGP_REQUIRE(nn_idx_host != nullptr, MGP_ERR_BAD_ARG, "nn_idx_host is required");
+  return fused_posterior_host_impl(p, nn_idx_host, nullptr, nullptr, query_idx_host, mean_host,
+                                   var_host, ws, ws_bytes, stream);
+}
+
+extern "C" int mgp_fused_posterior_host32(const mgp_problem* p, const int32_t* nn_idx_host32,
+                                          int32_t* nn_stage32, const int64_t* query_idx_host,
+                                          double* mean_host, double* var_host, void* ws,
+                                          size_t ws_bytes, void* stream) {
+  MGP_REQUIRE(nn_idx_host32 != nullptr, MGP_ERR_BAD_ARG, "nn_idx_host32 is required");
+  return fused_posterior_host_impl(p, nullptr, nn_idx_host32, nn_stage32, query_idx_host,
+                                   mean_host, var_host, ws, ws_bytes, stream);
 }

@@ -218,9 +218,13 @@ def fused_posterior(
     if ws_bytes:
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     if _host is not None:  # (nn_idx, query_idx, mean, var) CPU tensors; see fused_posterior_host
-        hp = [None if h is None else C.c_void_p(h.data_ptr()) for h in _host]
-        L.check(lib.mgp_fused_posterior_host(C.byref(p), hp[0], hp[1], hp[2], hp[3], _p(ws),
-                                             ws_bytes, _stream()))
+        hp = [None if h is None else C.c_void_p(h.data_ptr()) for h in _host[:4]]
+        if _host[0].dtype == torch.int32:  # 32-bit indices: int32 device staging buffer last
+            L.check(lib.mgp_fused_posterior_host32(C.byref(p), hp[0], _p(_host[4]), hp[1], hp[2],
+                                                   hp[3], _p(ws), ws_bytes, _stream()))
+        else:
+            L.check(lib.mgp_fused_posterior_host(C.byref(p), hp[0], hp[1], hp[2], hp[3], _p(ws),
+                                                 ws_bytes, _stream()))
         out["_host_buffers"] = _host  # keep them alive until the stream has been synchronised
         return out
     L.check(lib.mgp_fused_posterior(C.byref(p), _p(ws), ws_bytes, _stream()))
@@ -232,6 +236,8 @@ def fused_posterior_host(train_x, query_x, query_idx_host, nn_idx_host, train_y,
                          mean_host: Optional[torch.Tensor] = None,
                          var_host: Optional[torch.Tensor] = None, **kw):
     """K1 with the neighbour (and batch) indices in HOST memory: `mgp_fused_posterior_host`
+    (`mgp_fused_posterior_host32` when the neighbour indices are int32: they cross the host link
+    as they are and are widened on the device)
     uploads them chunk by chunk on two internal streams under the kernels of the previous
     chunks and, when `mean_host` / `var_host` (CPU float64 tensors, ideally pinned) are given,
     streams the results back the same way.  Returns the device tensors like fused_posterior;
@@ -239,13 +245,15 @@ def fused_posterior_host(train_x, query_x, query_idx_host, nn_idx_host, train_y,
     train_x = as_2d(fdev(train_x, "train_features"))
     dev = train_x.device
 
-    def host_i64(a, name):
+    def host_i64(a, name, keep32=False):
         t = torch.as_tensor(a)
         if t.is_cuda:
             raise TypeError(f"{name} must be a host array")
+        if keep32 and t.dtype == torch.int32:  # travels as is: half the bytes on the host link
+            return t.contiguous()
         return t.to(i64).contiguous()
 
-    nn_h = host_i64(nn_idx_host, "nn_indices")
+    nn_h = host_i64(nn_idx_host, "nn_indices", keep32=True)
     if nn_h.dim() != 2:
         raise ValueError(f"nn_indices must be (batch_count, nn_count), not {tuple(nn_h.shape)}")
     idx_h = None if query_idx_host is None else host_i64(query_idx_host, "indices")
@@ -254,8 +262,10 @@ def fused_posterior_host(train_x, query_x, query_idx_host, nn_idx_host, train_y,
             raise TypeError(f"{name} must be a contiguous host float64 tensor")
     nn_stage = torch.empty(nn_h.shape, dtype=i64, device=dev)
     idx_stage = None if idx_h is None else torch.empty(idx_h.shape, dtype=i64, device=dev)
+    nn_stage32 = (torch.empty(nn_h.shape, dtype=torch.int32, device=dev)
+                  if nn_h.dtype == torch.int32 else None)
     return fused_posterior(train_x, query_x, idx_stage, nn_stage, train_y,
-                           _host=(nn_h, idx_h, mean_host, var_host), **kw)
+                           _host=(nn_h, idx_h, mean_host, var_host, nn_stage32), **kw)
 
 
 class FusedLoo:

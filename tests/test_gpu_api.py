@@ -367,6 +367,48 @@ def test_host_buffer_pipeline_shapes(b, k, r, d, hetero):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("b,k", [(41_237, 50), (30_011, 13), (100, 7), (66_000, 100)])
+def test_host_buffer_pipeline_int32_indices(b, k):
+    """`mgp_fused_posterior_host32`: 32-bit neighbour indices cross the host link as they are and
+    are widened on the device chunk by chunk (odd k: chunk offsets that are not 16-byte aligned
+    take the scalar widening loop) -- bit for bit the single launch over int64 device indices,
+    from pinned and from pageable memory, and through `regress_from_indices`."""
+    import torch
+
+    from muygpys_b200 import ops
+    from muygpys_b200.examples.from_indices import regress_from_indices
+
+    rng = np.random.default_rng(b + k)
+    n = 40_000
+    x = torch.as_tensor(rng.uniform(size=(n, 2))).cuda()
+    y = torch.as_tensor(rng.normal(size=n)).cuda()
+    q = torch.as_tensor(rng.uniform(size=(b, 2))).cuda()
+    nn, _ = ops.knn(x, q, k)
+    kw = dict(kernel_id=2, metric_id=0, length_scale=0.1, noise=1e-3, scale=1.3)
+    want = ops.fused_posterior(x, q, None, nn, y, **kw)
+    nn32 = nn.cpu().to(torch.int32)
+    for src in (nn32.pin_memory(), nn32.numpy()):
+        got = ops.fused_posterior_host(x, q, None, src, y, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(got["mean"], want["mean"]) and torch.equal(got["var"], want["var"])
+    from muygpys_b200.gp import MuyGPS
+    from muygpys_b200.gp.deformation import Isotropy, l2
+    from muygpys_b200.gp.hyperparameter import FixedScale, Parameter
+    from muygpys_b200.gp.kernels import Matern
+    from muygpys_b200.gp.noise import HomoscedasticNoise
+
+    scale = FixedScale()
+    scale._set(1.3)
+    model = MuyGPS(kernel=Matern(smoothness=Parameter(1.5),
+                                 deformation=Isotropy(l2, Parameter(0.1))),
+                   noise=HomoscedasticNoise(1e-3), scale=scale)
+    mean, var = regress_from_indices(model, np.arange(b), nn32.numpy(), q, x, y)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.as_tensor(mean).cuda().reshape(-1), want["mean"][:, 0])
+    assert torch.equal(torch.as_tensor(var).cuda().reshape(-1), want["var"])
+
+
+@pytest.mark.gpu
 def test_host_buffer_pipeline_error_behaviour():
     """The host-buffer entry point rejects device index arrays and mismatched shapes loudly."""
     import torch

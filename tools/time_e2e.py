@@ -41,4 +41,8 @@ out["kernel_ms"] = timeit(lambda: ops.fused_posterior(x, q, None, nn, y, **kw))
 out["host_pipeline_ms"] = timeit(lambda: ops.fused_posterior_host(x, q, None, nn_pin, y, **kw))
 out["host_pipeline_with_d2h_ms"] = timeit(lambda: ops.fused_posterior_host(
     x, q, None, nn_pin, y, mean_host=mean_pin, var_host=var_pin, **kw))
-print(json.dumps(out))
+nn_pin32 = nn.cpu().to(torch.int32).pin_memory()
+out["host_pipeline_int32_ms"] = timeit(lambda: ops.fused_posterior_host(x, q, None, nn_pin32, y, **kw))
+out["host_pipeline_int32_with_d2h_ms"] = timeit(lambda: ops.fused_posterior_host(
+    x, q, None, nn_pin32, y, mean_host=mean_pin, var_host=var_pin, **kw))
+print(json.dumps({k_: round(v, 4) for k_, v in out.items()}))
