@@ -9,9 +9,13 @@ k = 50, tau^2 = 1e-3 -- at N GPUs of one node (weak scaling: every rank owns its
 
 One JSON line on stdout (rank 0).  A step is one pass of the hot path over the batch:
 `value` times the fused kernel with everything resident in HBM (L2 flushed between steps);
-`e2e` times the public call `regress_from_indices` with pinned HOST buffers, host<->device
-copies inside the timed region; `e2e_with_knn` times `regress_any` (test FEATURES in, exact KNN
-on the device, mean / variance out).  `roofline` is the fused kernel against the FP64 issue rate
+`e2e` times the public call `regress_any` (the reference's features-in call,
+S/examples/regress.py) with pinned HOST buffers, host<->device copies inside the timed region:
+test FEATURES in, exact KNN on the device, fused kernel, mean / variance out -- the neighbour
+indices never cross the host link, so it scales with the GPUs; `e2e_from_indices` times
+`regress_from_indices` with the precomputed int64 neighbour lists in pinned host memory (what
+the reference arm is handed; bound by the 42 MB index upload per step, and by the shared host
+link at N > 2), `e2e_int32_indices` the same with int32 lists.  `roofline` is the fused kernel against the FP64 issue rate
 MEASURED on this GPU (MEASURED_PEAKS.json has no FP64 entry, see tools/fp64_probe.py);
 `cpu_baseline` is the unmodified reference (MuyGPyS numpy backend) timed on the host cores on
 the same inputs; `loo` is the second half of the BASELINE metric (LOO objective evaluations/s)
@@ -513,14 +517,14 @@ def run_ours(args):
     # Python path per step): it keeps getting faster for ~10 steps after a cold start (host
     # clocks, page-locked buffers first touched by the copy engine), so it gets W + 8 warm-ups
     for _ in range(args.warmup + 8):
-        step_e2e()
+        step_e2e_knn()
     barrier()
     e_evs = []
     for _ in range(args.steps):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        step_e2e()
+        step_e2e_knn()
         b.record()
         e_evs.append((a, b))
     barrier()
@@ -533,7 +537,7 @@ def run_ours(args):
     clocks = sampler.stop(keep_loaded)
     e2e_steps_ms = [a.elapsed_time(b) for a, b in e_evs]
     e2e_ms_per_step = allmax(sum(e2e_steps_ms) / args.steps)
-    e2e_knn_ms = timed_ms(step_e2e_knn, max(5, args.steps // 2), warm=3)
+    e2e_idx_ms = timed_ms(step_e2e, args.steps, warm=args.warmup + 8)
     e2e_i32_ms = timed_ms(step_e2e_i32, args.steps, warm=5)
     # what the host link of this box gives for the same pinned index buffer (explains e2e)
     nn_stage = torch.empty_like(nn)
@@ -839,7 +843,7 @@ def run_ours(args):
                     c["scaled_to_10k_rows_evals_per_s"] = c["evals_per_s"] * rows_loo / LOO_BATCH
                     cpu_loo[lname] = c
         setup = {"knn_ms_100k_queries": knn_ms, "knn_index_build_seconds": knn_build_s,
-                 "neighbours": "exact KNN precomputed on device, not timed in `value` / `e2e`"}
+                 "neighbours": "exact KNN precomputed on device for `value` / `e2e_from_indices`; `e2e` runs it inside the timed step"}
         out = {
             "metric": "neighbourhoods/s (k=50 fused solve+posterior)",
             "value": value, "unit": "neighbourhoods/s", "n_gpus": world, "steps": args.steps,
@@ -848,35 +852,40 @@ def run_ours(args):
             "config": config_dict(world), "setup": setup,
             "e2e": {"value": world * N_TEST / (e2e_ms_per_step * 1e-3),
                     "unit": "neighbourhoods/s", "ms_per_step": e2e_ms_per_step,
-                    # (rank 0's individual steps: the host enqueues ~70 copies / launches /
-                    # events per step, so host jitter shows up here and not in `value`)
+                    # (rank 0's individual steps: the host enqueues the copies / launches of a
+                    # step one by one, so host jitter shows up here and not in `value`)
                     "ms_steps_rank0": [round(t, 4) for t in e2e_steps_ms],
                     "warmup_steps": args.warmup + 8,
-                    "h2d_bytes_per_step": int(N_TEST * D * 8 + N_TEST * K * 8 + N_TEST * 8),
+                    "h2d_bytes_per_step": int(N_TEST * D * 8),
                     "d2h_bytes_per_step": int(2 * N_TEST * 8),
-                    "h2d_link_gbs": h2d_gbs,
-                    "h2d_ms_at_link_rate": (N_TEST * D + N_TEST * K + N_TEST) * 8 / h2d_gbs / 1e6,
-                    "api": "muygpys_b200.examples.from_indices.regress_from_indices -> "
-                           "mgp_fused_posterior_host (chunked copy/compute pipeline in the "
-                           "C-ABI library); pinned host test features + int64 neighbour "
-                           "indices in, mean/var out"},
+                    "api": "muygpys_b200.examples.regress.regress_any (the reference's "
+                           "features-in call, S/examples/regress.py): pinned host test FEATURES "
+                           "in, exact KNN on the device (mgp_knn_grid), fused kernel, mean/var "
+                           "out to pinned host memory -- the neighbour indices never cross the "
+                           "host link.  Does MORE than the reference arm's step, whose "
+                           "neighbours are precomputed and untimed"},
+            "e2e_from_indices": {
+                "value": world * N_TEST / (e2e_idx_ms * 1e-3), "unit": "neighbourhoods/s",
+                "ms_per_step": e2e_idx_ms,
+                "h2d_bytes_per_step": int(N_TEST * D * 8 + N_TEST * K * 8 + N_TEST * 8),
+                "d2h_bytes_per_step": int(2 * N_TEST * 8),
+                "h2d_link_gbs": h2d_gbs,
+                "h2d_ms_at_link_rate": (N_TEST * D + N_TEST * K + N_TEST) * 8 / h2d_gbs / 1e6,
+                "api": "muygpys_b200.examples.from_indices.regress_from_indices -> "
+                       "mgp_fused_posterior_host (chunked copy/compute pipeline in the C-ABI "
+                       "library); pinned host test features + precomputed int64 neighbour "
+                       "indices in (exactly what the reference arm is handed), mean/var out; "
+                       "bound by the index upload, which shares the host link at N > 1"},
             "e2e_int32_indices": {
                 "value": world * N_TEST / (e2e_i32_ms * 1e-3), "unit": "neighbourhoods/s",
                 "ms_per_step": e2e_i32_ms,
                 "h2d_bytes_per_step": int(N_TEST * D * 8 + N_TEST * K * 4 + N_TEST * 8),
                 "d2h_bytes_per_step": int(2 * N_TEST * 8),
-                "api": "the `e2e` call with the neighbour indices held as int32 on the host "
-                       "(numpy index arrays of any integer dtype are valid reference inputs): "
-                       "mgp_fused_posterior_host32 uploads them as they are and widens each "
-                       "chunk on the device"},
-            "e2e_with_knn": {"value": world * N_TEST / (e2e_knn_ms * 1e-3),
-                             "unit": "neighbourhoods/s", "ms_per_step": e2e_knn_ms,
-                             "h2d_bytes_per_step": int(N_TEST * D * 8),
-                             "d2h_bytes_per_step": int(2 * N_TEST * 8),
-                             "api": "muygpys_b200.examples.regress.regress_any: pinned host test "
-                                    "FEATURES in, exact KNN on the device, fused kernel, mean/var "
-                                    "out -- the neighbour indices never cross the host link"},
-            "gpu_launches": args.steps,  # one fused_tp_kernel launch per timed step per rank
+                "api": "the `e2e_from_indices` call with the neighbour indices held as int32 on "
+                       "the host (numpy index arrays of any integer dtype are valid reference "
+                       "inputs): mgp_fused_posterior_host32 uploads them as they are and widens "
+                       "each chunk on the device"},
+            "gpu_launches": args.steps,  # one fused_tp_kernel launch per timed `value` step per rank
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
