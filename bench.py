@@ -854,7 +854,7 @@ def run_ours(args):
                     "unit": "neighbourhoods/s", "ms_per_step": e2e_ms_per_step,
                     # (rank 0's individual steps: the host enqueues the copies / launches of a
                     # step one by one, so host jitter shows up here and not in `value`)
-                    "ms_steps_rank0": [round(t, 4) for t in e2e_steps_ms],
+                    "ms_steps_rank0_first20": [round(t, 4) for t in e2e_steps_ms[:20]],
                     "warmup_steps": args.warmup + 8,
                     "h2d_bytes_per_step": int(N_TEST * D * 8),
                     "d2h_bytes_per_step": int(2 * N_TEST * 8),
