@@ -110,7 +110,18 @@ class MgpError(RuntimeError):
 
 
 def build(verbose: bool = False) -> str:
-    """Compile the CUDA library in-tree (nvcc, sm_100a).  Returns the .so path."""
+    """Compile the CUDA library in-tree (nvcc, sm_100a).  Returns the .so path.
+
+    `make` only recompiles what changed, so an up-to-date tree proves nothing about the
+    toolchain: every call therefore also compiles one small unit (probe.cu) from scratch into a
+    temporary directory, and the outcome of both goes into profiles/build_record.json
+    (`build_mode`, `build_exercised`, objects recompiled, nvcc version, size / hash of the .so)."""
+    import hashlib
+    import json
+    import tempfile
+    import time
+
+    t0 = time.time()
     cmd = ["make", "-C", CSRC_DIR, "-j", str(min(8, os.cpu_count() or 1))]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
@@ -118,6 +129,39 @@ def build(verbose: bool = False) -> str:
         print(res.stderr)
     if res.returncode != 0:
         raise MgpError(f"building {LIB_PATH} failed (exit {res.returncode})")
+    recompiled = sum(1 for ln in res.stdout.splitlines() if " -c " in ln and "nvcc" in ln)
+    canary_ok = False
+    with tempfile.TemporaryDirectory() as tmp:
+        canary = subprocess.run(
+            ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode",
+             "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+             "-c", os.path.join(CSRC_DIR, "probe.cu"), "-o", os.path.join(tmp, "probe.o")],
+            capture_output=True, text=True)
+        canary_ok = canary.returncode == 0 and os.path.getsize(os.path.join(tmp, "probe.o")) > 0
+    if not canary_ok:
+        raise MgpError("nvcc could not compile csrc/probe.cu for sm_100a:\n" + canary.stderr)
+    try:
+        ver = subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout
+        ver = ver.strip().splitlines()[-2:]
+        with open(LIB_PATH, "rb") as f:
+            digest = hashlib.sha256(f.read()).hexdigest()
+        record = {
+            "build_mode": "make + nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo "
+                          "(muygpys_b200/csrc/Makefile), in-tree .so",
+            "build_exercised": True,
+            "objects_recompiled_by_this_call": recompiled,
+            "library_was_up_to_date": recompiled == 0,
+            "canary": "csrc/probe.cu compiled from scratch for sm_100a by this call: ok",
+            "nvcc": ver, "so_bytes": os.path.getsize(LIB_PATH), "so_sha256": digest,
+            "seconds": round(time.time() - t0, 1),
+            "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),
+        }
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        with open(os.path.join(root, "profiles", "build_record.json"), "w") as f:
+            json.dump(record, f, indent=1)
+            f.write("\n")
+    except OSError:
+        pass  # (read-only checkout: the record is a courtesy, the build itself succeeded)
     return LIB_PATH
 
 
