@@ -169,8 +169,10 @@ int mgp_set_fused_variant(int32_t variant);
  * across ranks.  Replaces make_loo_crossval_fn's kernel + mean (+ scale + variance) + loss
  * sequence (S/optimize/objective.py:20-105, S/_src/optimize/loss/numpy.py:22-61,
  * S/_src/optimize/scale/numpy.py:9-15) for mse, lool and pseudo-Huber (MGP_LOSS_NONE gives the
- * scale partials only); looph is nonlinear in the analytic scale and keeps the two-pass path
- * (mgp_fused_posterior + mgp_loss_partials).  r == 1, d <= 3, 7 <= k <= 102, homoscedastic nugget
+ * scale partials only).  looph is nonlinear in the scale: with MGP_LOSS_LOOPH the launch takes
+ * sigma^2 from p->scale (a fixed scale, or the analytic scale of a previous MGP_LOSS_NONE
+ * launch), MGP_P_AUX receives sum 2 b^2 (sqrt(1 + e^2 / (b^2 sigma^2 v)) - 1) and MGP_P_SQERR_V
+ * the Huber-weighted sum e^2 / (v sqrt(1 + u)), so that value and gradient finish like lool.  r == 1, d <= 3, 7 <= k <= 102, homoscedastic nugget
  * (MGP_ERR_UNSUPPORTED otherwise).  `ws` must be ZERO-FILLED before its first use and handed
  * back unchanged afterwards (it carries a self-resetting arrival counter). */
 size_t mgp_fused_loo_workspace_bytes(const mgp_problem* p);
@@ -213,6 +215,7 @@ int mgp_fused_loo_peers(const mgp_problem* p, int32_t loss_id, double boundary_s
  * device or pinned host) receives, per slot t, the batch sums
  *   grad[5t+0] = sum 2 e dm        (e = mean - target)      -> d sum e^2           (mse)
  *   grad[5t+1] = sum 2 e dm / v    grad[5t+2] = sum e^2 dv / v^2    grad[5t+3] = sum dv / v
+ *   (MGP_LOSS_LOOPH: the terms of grad[5t+1] and grad[5t+2] carry the weight 1 / sqrt(1 + u))
  *   grad[5t+4] = sum d yky                                   -> d sigma^2 (analytic scale)
  * from which the host finishes d mse and d lool (muygpys_b200/objective.py).  grad == NULL is
  * mgp_fused_loo_peers.  The gradient sums are per rank: `partials` goes through the peer

@@ -204,10 +204,12 @@ extern "C" int mgp_fused_loo_grad(const mgp_problem* p, int32_t loss_id, double 
   if (rc != MGP_OK) return rc;
   MGP_REQUIRE(partials != nullptr, MGP_ERR_BAD_ARG, "partials is required");
   MGP_REQUIRE(loss_id == MGP_LOSS_NONE || loss_id == MGP_LOSS_MSE || loss_id == MGP_LOSS_LOOL ||
-                  loss_id == MGP_LOSS_PSEUDO_HUBER,
+                  loss_id == MGP_LOSS_PSEUDO_HUBER || loss_id == MGP_LOSS_LOOPH,
               MGP_ERR_UNSUPPORTED,
-              "mgp_fused_loo finishes mse, lool and pseudo-Huber in one launch (loss_id %d needs "
-              "the two-pass path)", loss_id);
+              "mgp_fused_loo finishes mse, lool, pseudo-Huber and (for a known scale) looph in "
+              "one launch (loss_id %d needs the two-pass path)", loss_id);
+  MGP_REQUIRE(loss_id != MGP_LOSS_LOOPH || p->scale > 0.0, MGP_ERR_BAD_ARG,
+              "looph: p->scale must hold the (positive) variance scale sigma^2");
   Model model;
   rc = make_model(p->kernel_id, p->metric_id, p->d, p->length_scale_count, p->length_scale,
                   &model);
@@ -220,7 +222,9 @@ extern "C" int mgp_fused_loo_grad(const mgp_problem* p, int32_t loss_id, double 
               "query_idx");
   MGP_REQUIRE(ws != nullptr && ws_bytes >= loo_ws_bytes(), MGP_ERR_WORKSPACE,
               "workspace of %zu bytes required", loo_ws_bytes());
-  MGP_REQUIRE(boundary_scale > 0.0 || loss_id != MGP_LOSS_PSEUDO_HUBER, MGP_ERR_BAD_ARG,
+  MGP_REQUIRE(boundary_scale > 0.0 ||
+                  (loss_id != MGP_LOSS_PSEUDO_HUBER && loss_id != MGP_LOSS_LOOPH),
+              MGP_ERR_BAD_ARG,
               "boundary_scale must be positive");
   ColLoo loo = {};
   if (g != nullptr && g->world > 1) {

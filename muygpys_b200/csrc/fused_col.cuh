@@ -736,7 +736,18 @@ __global__ void __launch_bounds__(COL_WARPS * 32, GRAD ? 3 : MGP_COL_MINB)
           acc[MGP_P_COUNT] += 1.0;
           acc[MGP_P_YKY] += out_yky;
           acc[MGP_P_ROWS] += 1.0;
-          acc[MGP_P_SQERR_V] += e2 / out_var;
+          // looph with a KNOWN scale sigma^2 = a.scale (S/_src/optimize/loss/numpy.py:82-97):
+          // 2 b^2 (sqrt(1 + e^2 / (b^2 sigma^2 v)) - 1) goes to AUX, its log(sigma^2 v) term comes
+          // from LOGV; the Huber weight 1 / sqrt(1 + u) multiplies the lool numerator and the two
+          // gradient sums built from it, so that the host finishes looph like lool.
+          double hw = 1.0;
+          if (loo.loss_id == MGP_LOSS_LOOPH) {
+            const double b2 = loo.boundary_scale * loo.boundary_scale;
+            const double root = sqrt(1.0 + e2 / (b2 * a.scale * out_var));
+            acc[MGP_P_AUX] += 2.0 * b2 * (root - 1.0);
+            hw = 1.0 / root;
+          }
+          acc[MGP_P_SQERR_V] += hw * e2 / out_var;
           acc[MGP_P_LOGV] += log(out_var);
           if (loo.loss_id == MGP_LOSS_PSEUDO_HUBER) {
             const double z = err / loo.boundary_scale;
@@ -749,8 +760,8 @@ __global__ void __launch_bounds__(COL_WARPS * 32, GRAD ? 3 : MGP_COL_MINB)
               if (t < D || t == 3) {
                 double* gr = acc + MGP_PARTIALS + 5 * t;
                 gr[0] += 2.0 * err * gdm[t];            // d sum e^2
-                gr[1] += 2.0 * err * gdm[t] * iv;        // sum 2 e dm / v
-                gr[2] += e2 * gdv[t] * iv * iv;          // sum e^2 dv / v^2
+                gr[1] += hw * 2.0 * err * gdm[t] * iv;        // sum w 2 e dm / v
+                gr[2] += hw * e2 * gdv[t] * iv * iv;          // sum w e^2 dv / v^2
                 gr[3] += gdv[t] * iv;                    // sum dv / v
                 gr[4] += gdy[t];                         // d sum yky
               }

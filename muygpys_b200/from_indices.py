@@ -119,7 +119,7 @@ def optimize_from_indices(muygps, batch_indices, batch_nn_indices, train_feature
 
         vg = make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                                               train_features, train_targets, group=group,
-                                              distributed=distributed)
+                                              distributed=distributed, loss_kwargs=loss_kwargs)
         return _lbfgsb_with_gradient(muygps, vg, verbose=verbose, **kwargs)
     obj_fn = make_fused_loo_crossval_fn(
         muygps, loss_fn, batch_indices, batch_nn_indices, train_features, train_targets,

@@ -3,9 +3,9 @@
 `make_loo_crossval_fn` keeps the reference's signature and works on materialised
 difference/distance tensors through the staged kernels.  `make_fused_loo_crossval_fn` is the
 fast path: it captures (features, indices, targets) instead and, for one response with the mse,
-lool or pseudo-Huber loss, every `obj_fn(**theta)` call is ONE kernel launch
-(`mgp_fused_loo`: K1 with the loss / scale partials folded into its epilogue) followed by a
-64-byte read -- with several ranks, the per-rank records are summed by one all-reduce
+lool, pseudo-Huber or looph loss, every `obj_fn(**theta)` call is ONE kernel launch
+(`mgp_fused_loo`: K1 with the loss / scale partials folded into its epilogue; looph with the
+analytic scale: one launch for sigma^2, one for the loss) followed by a 64-byte read -- with several ranks, the per-rank records are summed by one all-reduce
 (`distributed.PartialsReducer`).  Other shapes take K1 + the loss kernels.
 """
 
@@ -104,8 +104,10 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
         # y^T K^-1 y finish it after ONE reduction
         return float(rec[L.P_SQERR_V] / sigma2 + rec[L.P_LOGV] + rows * math.log(sigma2))
 
+    looph = loss_fn.loss_id == L.LOSS_LOOPH
     one_launch = (target_mask is None
-                  and loss_fn.loss_id in (L.LOSS_MSE, L.LOSS_LOOL, L.LOSS_PSEUDO_HUBER)
+                  and loss_fn.loss_id in (L.LOSS_MSE, L.LOSS_LOOL, L.LOSS_PSEUDO_HUBER,
+                                          L.LOSS_LOOPH)
                   and ops.fused_loo_supported(d, k, r, spec.kernel_id, spec.metric_id,
                                               spec.heteroscedastic)
                   and x.data_ptr() % 16 == 0)
@@ -129,7 +131,9 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
         def obj_fn(*args, **theta):
             ls = spec.length_scale_arg(**theta)
             rec_scale = None
-            if analytic and not same_noise(theta):
+            # (looph is nonlinear in sigma^2: the scale launch always comes first, and its
+            #  sigma^2 goes into the loss launch -- two launches, S/optimize/objective.py:94-105)
+            if analytic and (looph or not same_noise(theta)):
                 # reference quirk: the analytic scale perturbs with the MODEL's nugget, ignoring
                 # the optimiser's `noise=` (S/gp/hyperparameter/scale.py:206-208)
                 if not loo_scale:
@@ -138,6 +142,16 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                         loss_id=L.LOSS_NONE, partials=reducer.slot() if on_device else None))
                 rec_scale = read(loo_scale[0], loo_scale[0].launch(ls, model_noise, chan_scale),
                                  chan_scale is not None)
+            if looph:
+                if analytic:
+                    sigma2 = spec.sigma_from_mean_quadratic_form(
+                        rec_scale[L.P_YKY] / (rec_scale[L.P_ROWS] * k))
+                else:
+                    sigma2 = spec.scale()
+                rec = read(loo, loo.launch(ls, spec.noise(theta.get("noise")), chan,
+                                           scale=sigma2), chan is not None)
+                return -float(rec[L.P_AUX] + rec[L.P_LOGV]
+                              + rec[L.P_ROWS] * math.log(sigma2))
             rec = read(loo, loo.launch(ls, spec.noise(theta.get("noise")), chan),
                        chan is not None)
             return -finish(rec, rec_scale)
@@ -194,34 +208,45 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
 
 def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                                      train_features, train_targets, group=None,
-                                     distributed: bool = False) -> Callable:
+                                     distributed: bool = False,
+                                     loss_kwargs: Optional[Dict] = None) -> Callable:
     """`fn(**theta) -> (objective, {name: d objective / d name})` with the ANALYTIC gradient
     (SURVEY.md 8f-2): one launch of `mgp_fused_loo_grad` per call, where the reference's
     optimiser needs 1 + p objective evaluations for its finite differences
     (S/_src/optimize/chassis/numpy.py:68-74).  The objective is the negated loss, as
-    `make_loo_crossval_fn` returns it.  Supported: mse and lool (fixed scale, or analytic scale
-    with iteration_count == 1 and a fixed nugget), one response, the shapes of `mgp_fused_loo`.
+    `make_loo_crossval_fn` returns it.  Supported: mse, lool and looph (fixed scale, or analytic
+    scale with iteration_count == 1 and a fixed nugget), one response, the shapes of
+    `mgp_fused_loo`.  looph is nonlinear in the scale: with the analytic scale a plain launch
+    (y^T K^-1 y only) fixes sigma^2 first, then the gradient launch is handed that value -- two
+    launches, where finite differences take 2 (1 + p).
     Gradient names follow the optimiser's keywords: `length_scale` | `length_scale0..`,
     `noise`."""
     spec = ModelSpec.of(muygps)
     loss_fn = as_loss(loss_fn)
+    loss_kwargs = dict(loss_kwargs or {})
     x = fdev(train_features)
     y = fdev(train_targets)
     bi, bnn = idev(batch_indices), idev(batch_nn_indices)
     k = bnn.shape[1]
     d = 1 if x.dim() == 1 else x.shape[1]
     r = 1 if y.dim() == 1 else y.shape[1]
-    if loss_fn.loss_id not in (L.LOSS_MSE, L.LOSS_LOOL):
-        raise NotImplementedError(f"analytic gradient: loss {loss_fn.name} (mse and lool only)")
+    if loss_fn.loss_id not in (L.LOSS_MSE, L.LOSS_LOOL, L.LOSS_LOOPH):
+        raise NotImplementedError(
+            f"analytic gradient: loss {loss_fn.name} (mse, lool and looph only)")
     if not ops.fused_loo_supported(d, k, r, spec.kernel_id, spec.metric_id, spec.heteroscedastic,
                                    grad=True):
         raise NotImplementedError("analytic gradient: shape not supported by mgp_fused_loo_grad")
-    lool = loss_fn.loss_id == L.LOSS_LOOL
+    looph = loss_fn.loss_id == L.LOSS_LOOPH
+    lool = loss_fn.loss_id == L.LOSS_LOOL or looph  # (looph finishes like lool, weighted sums)
     analytic = lool and spec.analytic
     if analytic and spec.iteration_count != 1:
         raise NotImplementedError("analytic gradient with AnalyticScale(iteration_count > 1)")
+    delta = float(loss_kwargs.get("boundary_scale", loss_fn.default_boundary()))
     loo = ops.FusedLoo(x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
-                       loss_id=loss_fn.loss_id, want_grad=True)
+                       loss_id=loss_fn.loss_id, boundary_scale=delta, want_grad=True)
+    # looph with the analytic scale: sigma^2 from a plain launch before the gradient launch
+    loo_scale = (ops.FusedLoo(x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
+                              loss_id=L.LOSS_NONE) if looph and analytic else None)
     model_noise = spec.noise(None)
 
     def fn(*args, **theta):
@@ -229,8 +254,21 @@ def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_in
             raise NotImplementedError(
                 "analytic gradient: the analytic scale ignores the optimiser's nugget "
                 "(S/gp/hyperparameter/scale.py:206-208); optimise the nugget by finite differences")
-        rec = loo.record(loo.launch(spec.length_scale_arg(**theta),
-                                    spec.noise(theta.get("noise"))))
+        ls, nz = spec.length_scale_arg(**theta), spec.noise(theta.get("noise"))
+        sigma2 = None
+        if looph:
+            if analytic:
+                rs = loo_scale.record(loo_scale.launch(ls, nz))
+                if distributed:
+                    from .distributed import allreduce_partials
+
+                    rs_dev = torch.as_tensor(rs).to(x.device)
+                    allreduce_partials(rs_dev, group)
+                    rs = rs_dev.cpu().numpy()
+                sigma2 = spec.sigma_from_mean_quadratic_form(rs[L.P_YKY] / (rs[L.P_ROWS] * k))
+            else:
+                sigma2 = spec.scale()
+        rec = loo.record(loo.launch(ls, nz, scale=sigma2))
         g = loo.grad.numpy().reshape(L.MGP_GRAD_PARAMS, 5).copy()
         if distributed:
             from .distributed import allreduce_partials
@@ -241,9 +279,13 @@ def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_in
             rec, g = both[:8], both[8:].reshape(L.MGP_GRAD_PARAMS, 5)
         rows = rec[L.P_ROWS]
         if lool:
+            # (looph: SQERR_V and the gradient sums 1, 2 carry the Huber weight 1 / sqrt(1 + u),
+            #  AUX holds sum 2 b^2 (sqrt(1 + u) - 1): the same expressions finish both losses)
             S = rec[L.P_SQERR_V]
-            sigma2 = rec[L.P_YKY] / (rows * k) if analytic else spec.scale()
-            value = S / sigma2 + rec[L.P_LOGV] + rows * math.log(sigma2)
+            if sigma2 is None:
+                sigma2 = rec[L.P_YKY] / (rows * k) if analytic else spec.scale()
+            head = rec[L.P_AUX] if looph else S / sigma2
+            value = head + rec[L.P_LOGV] + rows * math.log(sigma2)
 
             def dloss(t):
                 dsig = t[4] / (rows * k) if analytic else 0.0

@@ -322,13 +322,17 @@ class FusedLoo:
         self._np = self.pinned.numpy()
         self._stream_obj = None
 
-    def launch(self, length_scale, noise: float, peers=None) -> torch.Tensor:
+    def launch(self, length_scale, noise: float, peers=None,
+               scale: Optional[float] = None) -> torch.Tensor:
         """Enqueue one evaluation on the current stream; returns the device partials record.
         `peers` (a distributed.PeerChannel): the record is summed across the GPUs of the NVLink
-        domain inside the same kernel (`mgp_fused_loo_peers`)."""
+        domain inside the same kernel (`mgp_fused_loo_peers`).  `scale`: the variance scale
+        sigma^2 the looph epilogue needs (MGP_LOSS_LOOPH reads it from p->scale)."""
         if self.x.device.index != torch.cuda.current_device():
             with torch.cuda.device(self.x.device):
-                return self.launch(length_scale, noise, peers)
+                return self.launch(length_scale, noise, peers, scale)
+        if scale is not None:
+            self.p.scale = float(scale)
         if isinstance(length_scale, float):
             self.ls_host[0] = length_scale
             self.p.length_scale_count = 1

@@ -57,6 +57,11 @@ CASES = [
     (0.5, [0.4, 0.3, 0.5], 3, 79, "lool", False, True),
     ("rbf", 0.2, 1, 88, "mse", False, True),
     (np.inf, 0.4, 2, 102, "lool", True, False),
+    # looph: Huber-weighted sums in the same epilogue; analytic scale = one extra plain launch
+    (1.5, 0.3, 2, 50, "looph", True, False),
+    (2.5, [0.3, 0.6], 2, 30, "looph", False, True),
+    (0.5, 0.3, 2, 100, "looph", True, False),
+    ("rbf", 0.2, 1, 23, "looph", False, True),
 ]
 
 
@@ -104,6 +109,30 @@ def test_gradient_against_oracle_objective():
     def oracle(l):
         return O.loo_objective(O.LOSS_LOOL, O.KERNEL_MATERN_15, O.METRIC_L2, l, 1e-3, x, y, bi,
                                bnn)[0]
+
+    assert abs(val - oracle(ls)) <= 1e-10 * abs(val)
+    h = 1e-5 * ls
+    fd = (oracle(ls + h) - oracle(ls - h)) / (2 * h)
+    assert abs(grads["length_scale"] - fd) <= 1e-6 * abs(fd), (grads, fd)
+
+
+def test_looph_gradient_against_oracle_objective():
+    """looph (analytic scale, boundary_scale = 2.5 through loss_kwargs) against central
+    differences of the oracle's objective."""
+    from muygpys_b200.optimize.loss import looph_fn
+    from muygpys_b200.optimize.objective import make_fused_loo_value_and_grad_fn
+
+    x, y, bi, bnn = _setup(6, 2000, 150, 2, 50)
+    y = y + 0.5 * (np.arange(len(y)) % 97 == 0)  # a few outliers: Huber weights well below 1
+    model = _model(1.5, 0.3, 1e-3, True)
+    vg = make_fused_loo_value_and_grad_fn(model, looph_fn, bi, bnn, x, y,
+                                          loss_kwargs={"boundary_scale": 2.5})
+    ls = 0.27
+    val, grads = vg(length_scale=ls)
+
+    def oracle(l):
+        return O.loo_objective(O.LOSS_LOOPH, O.KERNEL_MATERN_15, O.METRIC_L2, l, 1e-3, x, y, bi,
+                               bnn, loss_kwargs={"boundary_scale": 2.5})[0]
 
     assert abs(val - oracle(ls)) <= 1e-10 * abs(val)
     h = 1e-5 * ls
