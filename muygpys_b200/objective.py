@@ -215,8 +215,10 @@ def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_in
     optimiser needs 1 + p objective evaluations for its finite differences
     (S/_src/optimize/chassis/numpy.py:68-74).  The objective is the negated loss, as
     `make_loo_crossval_fn` returns it.  Supported: mse, lool and looph (fixed scale, or analytic
-    scale with iteration_count == 1 and a fixed nugget), one response, the shapes of
-    `mgp_fused_loo`.  looph is nonlinear in the scale: with the analytic scale a plain launch
+    scale with iteration_count == 1), one response, the shapes of
+    `mgp_fused_loo`, including the nugget under the analytic scale (the reference's quirk: sigma^2
+    is taken at the MODEL's nugget; when the optimiser's differs, a second gradient launch at the
+    model's nugget supplies sigma^2 and its derivatives).  looph is nonlinear in the scale: with the analytic scale a plain launch
     (y^T K^-1 y only) fixes sigma^2 first, then the gradient launch is handed that value -- two
     launches, where finite differences take 2 (1 + p).
     Gradient names follow the optimiser's keywords: `length_scale` | `length_scale0..`,
@@ -248,15 +250,38 @@ def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_in
     loo_scale = (ops.FusedLoo(x, y, bi, bnn, kernel_id=spec.kernel_id, metric_id=spec.metric_id,
                               loss_id=L.LOSS_NONE) if looph and analytic else None)
     model_noise = spec.noise(None)
+    # Reference quirk (S/gp/hyperparameter/scale.py:206-208): the analytic scale perturbs with
+    # the MODEL's nugget whatever `noise=` the optimiser passes.  So sigma^2 never depends on the
+    # optimiser's nugget (d sigma^2 / d noise = 0), and when the two differ sigma^2 and its
+    # length-scale derivatives come from a second gradient launch at the model's nugget.
+    loo_model = []
+
+    def sum_ranks(rec, g):
+        from .distributed import allreduce_partials
+
+        both = torch.as_tensor(np.concatenate((rec, g.ravel()))).to(x.device)
+        allreduce_partials(both, group)  # per-rank sums of the record and the gradient
+        both = both.cpu().numpy()
+        return both[:8], both[8:].reshape(L.MGP_GRAD_PARAMS, 5)
 
     def fn(*args, **theta):
-        if analytic and "noise" in theta and float(theta["noise"]) != float(model_noise):
-            raise NotImplementedError(
-                "analytic gradient: the analytic scale ignores the optimiser's nugget "
-                "(S/gp/hyperparameter/scale.py:206-208); optimise the nugget by finite differences")
         ls, nz = spec.length_scale_arg(**theta), spec.noise(theta.get("noise"))
-        sigma2 = None
-        if looph:
+        other_noise = (analytic and not spec.heteroscedastic and "noise" in theta
+                       and float(theta["noise"]) != float(model_noise))
+        sigma2, rec_s, g_s = None, None, None
+        if other_noise:
+            if not loo_model:
+                loo_model.append(ops.FusedLoo(x, y, bi, bnn, kernel_id=spec.kernel_id,
+                                              metric_id=spec.metric_id, loss_id=L.LOSS_NONE,
+                                              want_grad=True))
+            ev = loo_model[0]
+            rec_s = ev.record(ev.launch(ls, model_noise))
+            g_s = ev.grad.numpy().reshape(L.MGP_GRAD_PARAMS, 5).copy()
+            if distributed:
+                rec_s, g_s = sum_ranks(rec_s, g_s)
+            sigma2 = spec.sigma_from_mean_quadratic_form(
+                rec_s[L.P_YKY] / (rec_s[L.P_ROWS] * k))
+        elif looph:
             if analytic:
                 rs = loo_scale.record(loo_scale.launch(ls, nz))
                 if distributed:
@@ -268,15 +293,10 @@ def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_in
                 sigma2 = spec.sigma_from_mean_quadratic_form(rs[L.P_YKY] / (rs[L.P_ROWS] * k))
             else:
                 sigma2 = spec.scale()
-        rec = loo.record(loo.launch(ls, nz, scale=sigma2))
+        rec = loo.record(loo.launch(ls, nz, scale=sigma2 if looph else None))
         g = loo.grad.numpy().reshape(L.MGP_GRAD_PARAMS, 5).copy()
         if distributed:
-            from .distributed import allreduce_partials
-
-            both = torch.as_tensor(np.concatenate((rec, g.ravel()))).to(x.device)
-            allreduce_partials(both, group)  # per-rank sums of the record and the gradient
-            both = both.cpu().numpy()
-            rec, g = both[:8], both[8:].reshape(L.MGP_GRAD_PARAMS, 5)
+            rec, g = sum_ranks(rec, g)
         rows = rec[L.P_ROWS]
         if lool:
             # (looph: SQERR_V and the gradient sums 1, 2 carry the Huber weight 1 / sqrt(1 + u),
@@ -286,24 +306,30 @@ def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_in
                 sigma2 = rec[L.P_YKY] / (rows * k) if analytic else spec.scale()
             head = rec[L.P_AUX] if looph else S / sigma2
             value = head + rec[L.P_LOGV] + rows * math.log(sigma2)
+            g_sigma = g if g_s is None else g_s  # where d sum yky comes from
 
-            def dloss(t):
-                dsig = t[4] / (rows * k) if analytic else 0.0
+            def dloss(t, slot=None):
+                if not analytic or slot == 3:
+                    dsig = 0.0  # fixed scale; or the nugget, which sigma^2 ignores (quirk)
+                elif slot is None:
+                    dsig = g_sigma[:d, 4].sum() / (rows * k)
+                else:
+                    dsig = g_sigma[slot, 4] / (rows * k)
                 return ((t[1] - t[2]) / sigma2 + t[3]
                         + dsig * (-S / (sigma2 * sigma2) + rows / sigma2))
         else:
             value = rec[L.P_SQERR] / rec[L.P_COUNT]
 
-            def dloss(t):
+            def dloss(t, slot=None):
                 return t[0] / rec[L.P_COUNT]
 
         grads = {}
         if spec.anisotropic:
             for f in range(d):
-                grads[f"length_scale{f}"] = -float(dloss(g[f]))
+                grads[f"length_scale{f}"] = -float(dloss(g[f], f))
         else:
             grads["length_scale"] = -float(dloss(g[:d].sum(axis=0)))
-        grads["noise"] = -float(dloss(g[3]))
+        grads["noise"] = -float(dloss(g[3], 3))
         return -float(value), grads
 
     return fn

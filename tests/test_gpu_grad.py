@@ -62,6 +62,10 @@ CASES = [
     (2.5, [0.3, 0.6], 2, 30, "looph", False, True),
     (0.5, 0.3, 2, 100, "looph", True, False),
     ("rbf", 0.2, 1, 23, "looph", False, True),
+    # the nugget under the ANALYTIC scale: sigma^2 is taken at the model's nugget (reference
+    # quirk), so it does not move with the optimiser's `noise=`
+    (1.5, 0.3, 2, 50, "lool", True, True),
+    (2.5, [0.3, 0.6], 2, 38, "looph", True, True),
 ]
 
 
@@ -114,6 +118,43 @@ def test_gradient_against_oracle_objective():
     h = 1e-5 * ls
     fd = (oracle(ls + h) - oracle(ls - h)) / (2 * h)
     assert abs(grads["length_scale"] - fd) <= 1e-6 * abs(fd), (grads, fd)
+
+
+@pytest.mark.parametrize("loss,aniso", [("lool", False), ("looph", True), ("lool", True)])
+def test_gradient_with_an_optimiser_nugget_that_differs_from_the_models(loss, aniso):
+    """Analytic scale while the optimiser's `noise=` differs from the model's nugget: sigma^2 and
+    its length-scale derivatives come from a second gradient launch at the MODEL's nugget
+    (S/gp/hyperparameter/scale.py:206-208); checked against central differences of the fused
+    objective, which reproduces the quirk (golden `obj_*` cases), and of the oracle's."""
+    from muygpys_b200.optimize import loss as losses
+    from muygpys_b200.optimize.objective import (make_fused_loo_crossval_fn,
+                                                 make_fused_loo_value_and_grad_fn)
+
+    x, y, bi, bnn = _setup(21, 3000, 300, 2, 50)
+    model_noise = 2e-3
+    ls = [0.3, 0.5] if aniso else 0.3
+    model = _model(1.5, ls, model_noise, True)
+    lf = getattr(losses, f"{loss}_fn")
+    vg = make_fused_loo_value_and_grad_fn(model, lf, bi, bnn, x, y)
+    obj = make_fused_loo_crossval_fn(model, lf, bi, bnn, x, y)
+    theta = ({f"length_scale{i}": v * 1.1 for i, v in enumerate(ls)} if aniso
+             else {"length_scale": ls * 1.1})
+    theta["noise"] = 5e-3
+    val, grads = vg(**theta)
+    assert abs(val - obj(**theta)) <= 1e-12 * abs(val)
+    lid = O.LOSS_LOOL if loss == "lool" else O.LOSS_LOOPH
+    ls_now = np.array([theta[f"length_scale{i}"] for i in range(2)]) if aniso \
+        else theta["length_scale"]
+    want = O.loo_objective(lid, O.KERNEL_MATERN_15, O.METRIC_L2, ls_now, 5e-3, x, y, bi, bnn,
+                           model_noise=model_noise)[0]
+    assert abs(val - want) <= 1e-10 * abs(val)
+    for name in theta:
+        base = theta[name]
+        h = 1e-5 * base
+        fd = (obj(**dict(theta, **{name: base + h})) - obj(**dict(theta, **{name: base - h}))) \
+            / (2 * h)
+        assert abs(grads[name] - fd) <= 2e-6 * max(abs(fd), 1e-3 * abs(val) / base), (
+            name, grads[name], fd)
 
 
 def test_looph_gradient_against_oracle_objective():
