@@ -85,6 +85,11 @@ def _lbfgsb_with_gradient(muygps, value_and_grad, verbose=False, **kwargs):
 
     names, x0, bounds = muygps.get_opt_params()
     names = [str(n) for n in names]
+    for n in names:
+        if n != "noise" and not n.startswith("length_scale"):
+            raise NotImplementedError(
+                f"use_gradient=True: no analytic derivative with respect to {n!r} (length "
+                "scales and the nugget only); optimise it by finite differences")
 
     def fun(xv):
         val, grads = value_and_grad(**dict(zip(names, xv)))
