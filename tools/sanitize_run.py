@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small launches of every kernel family for compute-sanitizer (memcheck / racecheck /
-synccheck): thread-per-tile (plain, LOO epilogue; T <= 8 and T = 13), column-direct with
+synccheck): thread-per-tile (plain, LOO / looph epilogue, back substitution and gradient;
+T <= 8 and T = 13), int32 host-index pipeline, column-direct with
 lane-parallel steps (coefficients, gradient, variant 4), tile (register and shared-memory
 factor, Gram d > 8), generic, host pipeline, KNN (grid, small-d, tiled, Gram pre-filter), fast
 mean, losses, staged ops, label mask."""
@@ -28,11 +29,15 @@ for d, k, r in ((2, 50, 1), (1, 30, 1), (3, 23, 1), (2, 100, 1), (2, 50, 3), (20
         bi = dev(np.sort(rng.choice(n, b, replace=False)))
         bnn, _ = ops.knn(xd, xd[bi], k + 1)
         bnn = bnn[:, 1:].contiguous()
-        for want_grad in ((False, True) if k <= 62 else (False,)):
-            loo = ops.FusedLoo(xd, yd[:, 0].contiguous(), bi, bnn, kernel_id=2, metric_id=0,
-                               loss_id=L.LOSS_LOOL, want_grad=want_grad)
-            for _ in range(2):
-                loo.record(loo.launch(0.3, 1e-3))
+        for want_grad in (False, True):  # (GRAD instantiations: every tile count, T = 13 at k = 100)
+            for loss_id in (L.LOSS_LOOL, L.LOSS_LOOPH):
+                loo = ops.FusedLoo(xd, yd[:, 0].contiguous(), bi, bnn, kernel_id=2, metric_id=0,
+                                   loss_id=loss_id, boundary_scale=3.0, want_grad=want_grad)
+                for _ in range(2):
+                    loo.record(loo.launch(0.3, 1e-3, scale=0.8))
+        # fast-mean coefficients from the back substitution (k = 100: GRAD, T = 13)
+        ops.fused_posterior(xd, xd, bi, bnn, yd, kernel_id=2, metric_id=0, length_scale=0.3,
+                            noise=1e-3, want_coeffs=True)
 # host pipeline
 x, q, y = rng.uniform(size=(20000, 2)), rng.uniform(size=(20000, 2)), rng.normal(size=20000)
 xd, qd, yd = dev(x), dev(q), dev(y)
@@ -42,6 +47,12 @@ nn, _ = nb.get_nns(qd)
 out = ops.fused_posterior_host(xd, qd, torch.arange(20000), nn.cpu(), yd, kernel_id=2, metric_id=0,
                                length_scale=0.1, noise=1e-3)
 torch.cuda.synchronize()
+# int32 host indices: widened on the device chunk by chunk (odd k: unaligned chunk offsets)
+for kk in (50, 13):
+    nn_k = nn[:, :kk].contiguous()
+    out = ops.fused_posterior_host(xd, qd, None, nn_k.cpu().to(torch.int32), yd, kernel_id=2,
+                                   metric_id=0, length_scale=0.1, noise=1e-3)
+    torch.cuda.synchronize()
 nb.get_batch_nns(torch.arange(0, 20000, 7).cuda())
 # high-d KNN paths
 x, q = rng.normal(size=(5000, 40)), rng.normal(size=(300, 40))
