@@ -704,6 +704,9 @@ __global__ void __launch_bounds__((TP_UWARPS + 1) * 32, 1)
     //     of that row; they are free once the last column of the previous neighbourhood is built
     auto prep_compact = [&](int nbuf) {
       if (T > 1) {
+        // T = 2: nothing else separates the previous neighbourhood's last finished-tile store
+        // (finish_column, slot 0) from these stores to the same slot by other lanes (racecheck)
+        if (T == 2) __syncwarp();
         // lane l evaluates columns l, l + 32, ... of three rows at a time: six entries in
         // flight, no index arithmetic, the column points loaded once (a flat 32-entries-per-pass
         // list took 2 200 cycles for 144 entries: three dependent passes, a division per entry)
