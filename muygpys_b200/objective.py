@@ -206,6 +206,55 @@ def make_fused_loo_crossval_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
     return obj_fn
 
 
+def finish_value_and_grad(rec, g, *, loss_id, k, d, anisotropic, analytic, sigma2=None,
+                          fixed_scale=None, g_sigma=None):
+    """Objective (negated loss) and its gradient from the summed records of `mgp_fused_loo_grad`:
+    `rec` the MGP_P_* partials, `g[t]` the five gradient sums of parameter slot t (length scale
+    of feature 0..2, nugget in slot 3; include/muygpys_b200.h).  Pure host arithmetic (tested on
+    the CPU against finite differences of the oracle, tests/test_grad_finish_cpu.py).
+
+    mse: sum e^2 / count.  lool: S / sigma^2 + sum log v + n log sigma^2 with S = sum e^2 / v.
+    looph: the kernel was handed sigma^2 and weighted S and the sums g[t][1], g[t][2] with the
+    Huber weight 1 / sqrt(1 + u), u = e^2 / (b^2 sigma^2 v); AUX = sum 2 b^2 (sqrt(1 + u) - 1)
+    replaces S / sigma^2 and the derivative keeps lool's form.  Analytic scale: sigma^2 =
+    sum yky / (n k) and d sigma^2 = sum d yky / (n k), taken from `g_sigma` when the scale was
+    evaluated in a separate launch at the MODEL's nugget (reference quirk,
+    S/gp/hyperparameter/scale.py:206-208); the optimiser's nugget never moves sigma^2."""
+    rows = rec[L.P_ROWS]
+    looph = loss_id == L.LOSS_LOOPH
+    if loss_id in (L.LOSS_LOOL, L.LOSS_LOOPH):
+        S = rec[L.P_SQERR_V]
+        if sigma2 is None:
+            sigma2 = rec[L.P_YKY] / (rows * k) if analytic else fixed_scale
+        head = rec[L.P_AUX] if looph else S / sigma2
+        value = head + rec[L.P_LOGV] + rows * math.log(sigma2)
+        gs = g if g_sigma is None else g_sigma  # where d sum yky comes from
+
+        def dloss(t, slot=None):
+            if not analytic or slot == 3:
+                dsig = 0.0  # fixed scale; or the nugget, which sigma^2 ignores (quirk)
+            elif slot is None:
+                dsig = gs[:d, 4].sum() / (rows * k)
+            else:
+                dsig = gs[slot, 4] / (rows * k)
+            return ((t[1] - t[2]) / sigma2 + t[3]
+                    + dsig * (-S / (sigma2 * sigma2) + rows / sigma2))
+    else:
+        value = rec[L.P_SQERR] / rec[L.P_COUNT]
+
+        def dloss(t, slot=None):
+            return t[0] / rec[L.P_COUNT]
+
+    grads = {}
+    if anisotropic:
+        for f in range(d):
+            grads[f"length_scale{f}"] = -float(dloss(g[f], f))
+    else:
+        grads["length_scale"] = -float(dloss(g[:d].sum(axis=0)))
+    grads["noise"] = -float(dloss(g[3], 3))
+    return -float(value), grads
+
+
 def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_indices,
                                      train_features, train_targets, group=None,
                                      distributed: bool = False,
@@ -297,39 +346,10 @@ def make_fused_loo_value_and_grad_fn(muygps, loss_fn, batch_indices, batch_nn_in
         g = loo.grad.numpy().reshape(L.MGP_GRAD_PARAMS, 5).copy()
         if distributed:
             rec, g = sum_ranks(rec, g)
-        rows = rec[L.P_ROWS]
-        if lool:
-            # (looph: SQERR_V and the gradient sums 1, 2 carry the Huber weight 1 / sqrt(1 + u),
-            #  AUX holds sum 2 b^2 (sqrt(1 + u) - 1): the same expressions finish both losses)
-            S = rec[L.P_SQERR_V]
-            if sigma2 is None:
-                sigma2 = rec[L.P_YKY] / (rows * k) if analytic else spec.scale()
-            head = rec[L.P_AUX] if looph else S / sigma2
-            value = head + rec[L.P_LOGV] + rows * math.log(sigma2)
-            g_sigma = g if g_s is None else g_s  # where d sum yky comes from
-
-            def dloss(t, slot=None):
-                if not analytic or slot == 3:
-                    dsig = 0.0  # fixed scale; or the nugget, which sigma^2 ignores (quirk)
-                elif slot is None:
-                    dsig = g_sigma[:d, 4].sum() / (rows * k)
-                else:
-                    dsig = g_sigma[slot, 4] / (rows * k)
-                return ((t[1] - t[2]) / sigma2 + t[3]
-                        + dsig * (-S / (sigma2 * sigma2) + rows / sigma2))
-        else:
-            value = rec[L.P_SQERR] / rec[L.P_COUNT]
-
-            def dloss(t, slot=None):
-                return t[0] / rec[L.P_COUNT]
-
-        grads = {}
-        if spec.anisotropic:
-            for f in range(d):
-                grads[f"length_scale{f}"] = -float(dloss(g[f], f))
-        else:
-            grads["length_scale"] = -float(dloss(g[:d].sum(axis=0)))
-        grads["noise"] = -float(dloss(g[3], 3))
-        return -float(value), grads
+        return finish_value_and_grad(
+            rec, g, loss_id=loss_fn.loss_id, k=k, d=d, anisotropic=spec.anisotropic,
+            analytic=analytic, sigma2=sigma2,
+            fixed_scale=spec.scale() if (lool and not analytic) else None,
+            g_sigma=g_s)
 
     return fn
