@@ -138,3 +138,29 @@ def test_finish_value_and_grad_matches_oracle_finite_differences(loss, analytic,
     for name, want_d in checks.items():
         assert abs(grads[name] - want_d) <= 2e-5 * max(abs(want_d), 1e-6 * abs(want)), (
             name, grads[name], want_d)
+
+
+@pytest.mark.parametrize("loss", ["lool", "looph"])
+def test_rank_shards_sum_to_the_full_batch(loss):
+    """N > 1: every rank's launch covers its shard of the batch rows, the records and gradient
+    sums are added across ranks (peer exchange / all-reduce) and finished once -- the result
+    must be the full batch's (the sums are linear in the rows; sigma^2 is global)."""
+    x, y, bi, bnn = _data()
+    loss_id = {"lool": L.LOSS_LOOL, "looph": L.LOSS_LOOPH}[loss]
+    ls, noise = [0.3, 0.45], 2e-3
+    _, _, yky = _rows(x, y, bi, bnn, ls, noise)
+    sigma2 = yky.sum() / (B * K)  # (looph: fixed by the global scale launch before the loss launch)
+    full = _kernel_sums(x, y, bi, bnn, ls, noise, loss_id, sigma2)
+    half = B // 2
+    parts = [_kernel_sums(x, y, bi[s], bnn[s], ls, noise, loss_id, sigma2)
+             for s in (slice(0, half), slice(half, B))]
+    rec = parts[0][0] + parts[1][0]
+    g = parts[0][1] + parts[1][1]
+    np.testing.assert_allclose(rec, full[0], rtol=1e-12)
+    kw = dict(loss_id=loss_id, k=K, d=D, anisotropic=True, analytic=True,
+              sigma2=sigma2 if loss == "looph" else None)
+    v_sum, g_sum = finish_value_and_grad(rec, g, **kw)
+    v_full, g_full = finish_value_and_grad(*full, **kw)
+    assert abs(v_sum - v_full) <= 1e-12 * abs(v_full)
+    for name in g_full:
+        assert abs(g_sum[name] - g_full[name]) <= 1e-9 * max(abs(g_full[name]), 1e-9)
